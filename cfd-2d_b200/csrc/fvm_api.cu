@@ -1,0 +1,638 @@
+// fvm_api.cu -- the C-ABI of include/cfd2d_fvm.h: handle, uploads, step orchestration (CUDA graph),
+// per-kernel timing, halo exchange (NCCL, loaded at run time).  No CPU numerics live here: every
+// number the caller gets back was produced by the kernels in fvm_kernels.cuh.
+#include "../../include/cfd2d_fvm.h"
+#include "fvm_kernels.cuh"
+#include "halo_nccl.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+static thread_local std::string g_create_error;
+
+struct cfd2d_fvm {
+    int device = 0;
+    int nc = 0, nc_ex = 0, ne = 0, nmat = 0, nbc = 0;
+    cfd2d_ctrl ctrl{};
+    KParams P{};
+    double TAU = 0.0, t = 0.0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    // device buffers
+    std::vector<void*> allocs;
+    double4 *Ua = nullptr, *Ub = nullptr, *W = nullptr, *G = nullptr, *F = nullptr;
+    double* io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // SoA staging for set/get
+    unsigned long long* tau_bits = nullptr;
+    int* err = nullptr;
+    // graph
+    bool use_graph = true;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double prof_ms[CFD2D_NKERNELS] = {0};
+    int64_t prof_n[CFD2D_NKERNELS] = {0};
+    int64_t launches = 0;
+    // halo
+    HaloNccl* halo = nullptr;
+    std::string error;
+};
+
+#define CUDA_TRY(h, call)                                                                  \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            char b_[512];                                                                  \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (h) (h)->error = b_; else g_create_error = b_;                              \
+            return CFD2D_ECUDA;                                                            \
+        }                                                                                  \
+    } while (0)
+
+template <class T>
+static int dev_alloc(cfd2d_fvm* h, T** p, size_t n) {
+    void* q = nullptr;
+    CUDA_TRY(h, cudaMalloc(&q, (n ? n : 1) * sizeof(T)));
+    h->allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+}
+
+template <class T>
+static int dev_upload(cfd2d_fvm* h, const T** p, const std::vector<T>& v) {
+    T* q = nullptr;
+    int rc = dev_alloc(h, &q, v.size());
+    if (rc) return rc;
+    if (!v.empty()) CUDA_TRY(h, cudaMemcpy(q, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *p = q;
+    return 0;
+}
+
+static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
+
+// rim_orig's constants, by the reference's own expressions (global.cpp:235-249)
+static RimC make_rim(double GAM) {
+    RimC k;
+    k.GAM = GAM;
+    k.AGAM = (GAM - 1.0);
+    k.DGAM = (2.0 / k.AGAM);
+    k.GGAM = (sqrt(GAM * k.AGAM));
+    k.HGAM = (k.AGAM / 2.0);
+    k.FGAM = (3.0 * GAM - 1.0);
+    k.OGAM = (k.AGAM / (2.0 * GAM));
+    k.QGAM = (GAM + 1.0);
+    k.PGAM = (k.QGAM / (2.0 * GAM));
+    k.RGAM = (4.0 * GAM);
+    k.SGAM = (GAM * k.AGAM);
+    k.TGAM = (k.QGAM / 2.0);
+    k.IAGAM = (1 / k.AGAM);
+    k.DG1 = (1 + k.DGAM);
+    k.DGGG = k.DGAM * k.GGAM;
+    return k;
+}
+
+// ---- kernel launch helpers with optional per-kernel event timing ---------------------------
+struct KTimer {
+    cfd2d_fvm* h; int id;
+    KTimer(cfd2d_fvm* h_, int id_) : h(h_), id(id_) { if (h->profiling) cudaEventRecord(h->ev0, h->stream); }
+    ~KTimer() {
+        h->launches++;
+        if (h->profiling) {
+            cudaEventRecord(h->ev1, h->stream);
+            cudaEventSynchronize(h->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+            h->prof_ms[id] += ms;
+            h->prof_n[id]++;
+        }
+    }
+};
+
+static void launch_prim(cfd2d_fvm* h, const double4* U, int c0, int c1) {
+    if (c1 <= c0) return;
+    h->launches++;
+    k_prim<<<nblk(c1 - c0, 256), 256, 0, h->stream>>>(h->P, U, h->W, c0, c1);
+}
+
+static void launch_grad(cfd2d_fvm* h) {
+    if (h->nc == 0) return;
+    KTimer t(h, CFD2D_K_GRAD);
+    k_grad<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->W, h->G);
+}
+
+static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale) {
+    if (h->ne == 0) return;
+    KTimer t(h, CFD2D_K_FLUX);
+    dim3 g(nblk(h->ne, 128)), b(128);
+    int fx = h->ctrl.flux, od = h->ctrl.order;
+    if (fx == CFD2D_FLUX_GODUNOV && od == 2) k_flux<0, 2><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
+    else if (fx == CFD2D_FLUX_GODUNOV) k_flux<0, 1><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
+    else if (od == 2) k_flux<1, 2><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
+    else k_flux<1, 1><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
+}
+
+static void launch_update(cfd2d_fvm* h, int stage) {
+    if (h->nc == 0) return;
+    KTimer t(h, stage == 1 ? CFD2D_K_UPDATE1 : CFD2D_K_UPDATE2);
+    if (stage == 1) k_update<1><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->F, h->Ua, h->Ub, h->W);
+    else k_update<2><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->F, h->Ub, h->Ua, h->W);
+}
+
+static void launch_remediate(cfd2d_fvm* h) {
+    KTimer t(h, CFD2D_K_REMEDIATE);
+    k_remediate<<<1, 1024, 0, h->stream>>>(h->P, h->Ua, h->W);
+}
+
+static void launch_tau_steady(cfd2d_fvm* h) {
+    if (h->nc == 0) return;
+    KTimer t(h, CFD2D_K_TIMESTEP);
+    k_tau_steady<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->W);
+}
+
+// halo exchange of U4 (rec4 = 1) into `U`'s halo slice followed by the halo prim conversion, or of
+// G8 (rec4 = 2).  Method::exchange semantics (method.h:13-41): recv lands contiguously at recvShift.
+static int exchange_U(cfd2d_fvm* h, double4* U) {
+    if (!h->halo) return 0;
+    KTimer t(h, CFD2D_K_HALO);
+    int rc = halo_exchange(h->halo, U, 1, h->stream, &h->launches);
+    if (rc) { h->error = halo_error(h->halo); return rc; }
+    launch_prim(h, U, h->nc, h->nc_ex);
+    return 0;
+}
+
+static int exchange_G(cfd2d_fvm* h) {
+    if (!h->halo || h->ctrl.order != 2) return 0;
+    KTimer t(h, CFD2D_K_HALO);
+    int rc = halo_exchange(h->halo, h->G, 2, h->stream, &h->launches);
+    if (rc) h->error = halo_error(h->halo);
+    return rc;
+}
+
+// One whole RK2 step = the body of the while loop of FVM_TVD::run (fvm_tvd.cpp:310-450).
+static int enqueue_step(cfd2d_fvm* h) {
+    int rc;
+    if (h->ctrl.steady) launch_tau_steady(h);                 // :315
+    // stage 1 (:323-374): W == prim(Ua) is valid on owned + halo cells here
+    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h))) return rc; }
+    launch_flux(h, h->Ua, 1);
+    launch_update(h, 1);                                       // Ub, W
+    if ((rc = exchange_U(h, h->Ub))) return rc;
+    // stage 2 (:376-427) + half-sum + limits (:430-447)
+    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h))) return rc; }
+    launch_flux(h, h->Ub, 1);
+    launch_update(h, 2);                                       // Ua, W, flags
+    if ((rc = exchange_U(h, h->Ua))) return rc;
+    launch_remediate(h);                                       // :449 (no-op kernel when nothing is flagged)
+    return 0;
+}
+
+static void drop_graph(cfd2d_fvm* h) {
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (h->graph) { cudaGraphDestroy(h->graph); h->graph = nullptr; }
+}
+
+static int check_device_errors(cfd2d_fvm* h) {
+    int e[2] = {0, 0};
+    CUDA_TRY(h, cudaMemcpyAsync(e, h->err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (e[0] != 0) {
+        char b[256];
+        snprintf(b, sizeof b, "rim_orig Newton iteration hit the cap (%d) on %d edge evaluations: non-physical "
+                 "left/right states (the reference would loop forever here)", h->P.max_newton, e[0]);
+        h->error = b;
+        cudaMemsetAsync(h->err, 0, sizeof(int), h->stream);
+        return CFD2D_ENEWTON;
+    }
+    return 0;
+}
+
+extern "C" {
+
+const char* cfd2d_version(void) { return "cfd2d_b200 0.1 (sm_100a)"; }
+
+const char* cfd2d_fvm_last_error(const cfd2d_fvm* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl* c, const cfd2d_halo* halo,
+                     int device, cfd2d_fvm** out) {
+    g_create_error.clear();
+    if (!m || !p || !c || !out) { g_create_error = "null argument"; return CFD2D_EINVAL; }
+    *out = nullptr;
+    if (m->nc < 0 || m->nc_ex < m->nc || m->ne < 0 || p->nmat < 1 || p->nmat > 255 || p->nbc < 0) {
+        g_create_error = "inconsistent sizes (nc, nc_ex, ne, nmat, nbc)";
+        return CFD2D_EINVAL;
+    }
+    if (c->order != 1 && c->order != 2) { g_create_error = "ctrl.order must be 1 or 2"; return CFD2D_EINVAL; }
+    if (c->flux != CFD2D_FLUX_GODUNOV && c->flux != CFD2D_FLUX_LAX) { g_create_error = "ctrl.flux must be GODUNOV or LAX"; return CFD2D_EINVAL; }
+    const int nc = m->nc, nc_ex = m->nc_ex, ne = m->ne;
+    // ---- validate topology on the host (cheap, once)
+    for (int e = 0; e < ne; e++) {
+        int c1 = m->edge_c1[e], c2 = m->edge_c2[e];
+        if (c1 < 0 || c1 >= nc_ex || c2 < -1 || c2 >= nc_ex) { g_create_error = "edge references a cell out of range"; return CFD2D_EINVAL; }
+        if (c2 < 0) {
+            int ib = m->edge_bc[e];
+            if (ib < 0 || ib >= p->nbc) {
+                char b[128];
+                snprintf(b, sizeof b, "Not defined boundary condition for edge %d", e);   // fvm_tvd.cpp:708
+                g_create_error = b;
+                return CFD2D_EBC;
+            }
+            int kind = p->bc_kind[ib];
+            if (kind < CFD2D_BC_INLET || kind > CFD2D_BC_WALL) { g_create_error = "unknown boundary kind"; return CFD2D_EBC; }
+        }
+    }
+    for (int i = 0; i < nc_ex; i++)
+        if (m->cell_mat[i] < 0 || m->cell_mat[i] >= p->nmat) { g_create_error = "cell material index out of range"; return CFD2D_EINVAL; }
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        g_create_error = "no usable CUDA device (this path has no CPU fallback)";
+        return CFD2D_ENODEV;
+    }
+    CUDA_TRY((cfd2d_fvm*)nullptr, cudaSetDevice(device));
+
+    cfd2d_fvm* h = new cfd2d_fvm();
+    h->device = device; h->nc = nc; h->nc_ex = nc_ex; h->ne = ne; h->nmat = p->nmat; h->nbc = p->nbc;
+    h->ctrl = *c;
+    if (h->ctrl.max_newton <= 0) h->ctrl.max_newton = 1000;
+    h->TAU = c->TAU;
+    int rc = 0;
+#define TRY(x) do { rc = (x); if (rc) { g_create_error = h->error.empty() ? g_create_error : h->error; cfd2d_fvm_destroy(h); return rc; } } while (0)
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return CFD2D_ECUDA; }
+        cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
+    }
+    // ---- per (cell, slot) gather tables
+    std::vector<int> s_nb(3 * (size_t)nc), s_es(3 * (size_t)nc);
+    std::vector<double> s_nx(3 * (size_t)nc), s_ny(3 * (size_t)nc), s_l(3 * (size_t)nc);
+    for (int cc = 0; cc < nc; cc++) {
+        for (int k = 0; k < 3; k++) {
+            int e = m->cell_edges[3 * (size_t)cc + k];
+            if (e < 0 || e >= ne) { g_create_error = "cell_edges entry out of range"; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
+            size_t o = (size_t)k * nc + cc;
+            if (m->edge_c1[e] == cc) {
+                s_nb[o] = m->edge_c2[e] >= 0 ? m->edge_c2[e] : -1 - m->edge_bc[e];
+                s_nx[o] = m->edge_nx[e]; s_ny[o] = m->edge_ny[e];
+                s_es[o] = e * 2;
+            } else if (m->edge_c2[e] == cc) {
+                s_nb[o] = m->edge_c1[e];
+                s_nx[o] = -m->edge_nx[e]; s_ny[o] = -m->edge_ny[e];
+                s_es[o] = e * 2 + 1;
+            } else {
+                g_create_error = "cell_edges names an edge that does not touch the cell";
+                cfd2d_fvm_destroy(h);
+                return CFD2D_EINVAL;
+            }
+            s_l[o] = m->edge_l[e];
+        }
+    }
+    // ---- per edge tables
+    std::vector<int2> e_c(ne);
+    std::vector<double2> e_n(ne);
+    std::vector<double> e_l2(ne);
+    std::vector<double4> e_d1(ne), e_d2(ne);
+    for (int e = 0; e < ne; e++) {
+        int c1 = m->edge_c1[e], c2 = m->edge_c2[e];
+        e_c[e] = make_int2(c1, c2);
+        e_n[e] = make_double2(m->edge_nx[e], m->edge_ny[e]);
+        e_l2[e] = m->edge_l[e] * 0.5;                                 // fvm_tvd.cpp:335
+        const double* g = m->edge_gp + 4 * (size_t)e;
+        // DL = PE - P(cell) (fvm_tvd.cpp:661-664): the same subtraction, done once
+        e_d1[e] = make_double4(g[0] - m->cell_cx[c1], g[1] - m->cell_cy[c1], g[2] - m->cell_cx[c1], g[3] - m->cell_cy[c1]);
+        if (c2 >= 0) e_d2[e] = make_double4(g[0] - m->cell_cx[c2], g[1] - m->cell_cy[c2], g[2] - m->cell_cx[c2], g[3] - m->cell_cy[c2]);
+        else e_d2[e] = make_double4(0, 0, 0, 0);
+    }
+    std::vector<MatC> mats(p->nmat);
+    for (int i = 0; i < p->nmat; i++) {
+        MatC q;
+        q.M = p->mat_M[i];
+        q.Cv = p->mat_Cp[i] - CFD2D_GR / p->mat_M[i];   // global.cpp:11
+        q.gam = p->mat_Cp[i] / q.Cv;                    // global.cpp:12
+        q.gm1 = q.gam - 1;
+        mats[i] = q;
+    }
+    std::vector<unsigned char> cmat(nc_ex);
+    for (int i = 0; i < nc_ex; i++) cmat[i] = (unsigned char)m->cell_mat[i];
+    std::vector<int> bkind(p->bc_kind, p->bc_kind + p->nbc);
+    std::vector<double> bpar(p->bc_par, p->bc_par + 4 * (size_t)p->nbc);
+    std::vector<double> cS(m->cell_S, m->cell_S + nc_ex);
+    std::vector<int> ebc(m->edge_bc, m->edge_bc + ne);
+
+    KParams& P = h->P;
+    P.nc = nc; P.nc_ex = nc_ex; P.ne = ne; P.nmat = p->nmat;
+    P.order = c->order; P.flux = c->flux; P.max_newton = h->ctrl.max_newton; P.steady = c->steady;
+    P.CFL = c->CFL;
+    memcpy(P.lim, p->limits, sizeof P.lim);
+    P.rim = make_rim(1.4);                               // double __GAM = 1.4; fvm_tvd.cpp:345
+    TRY(dev_upload(h, &P.mat, mats));
+    TRY(dev_upload(h, &P.bc_kind, bkind));
+    TRY(dev_upload(h, &P.bc_par, bpar));
+    TRY(dev_upload(h, &P.cell_mat, cmat));
+    TRY(dev_upload(h, &P.s_nb, s_nb));
+    TRY(dev_upload(h, &P.s_nx, s_nx));
+    TRY(dev_upload(h, &P.s_ny, s_ny));
+    TRY(dev_upload(h, &P.s_l, s_l));
+    TRY(dev_upload(h, &P.s_es, s_es));
+    TRY(dev_upload(h, &P.cell_S, cS));
+    TRY(dev_upload(h, &P.e_c, e_c));
+    TRY(dev_upload(h, &P.e_n, e_n));
+    TRY(dev_upload(h, &P.e_l2, e_l2));
+    TRY(dev_upload(h, &P.e_d1, e_d1));
+    TRY(dev_upload(h, &P.e_d2, e_d2));
+    TRY(dev_upload(h, &P.e_bc, ebc));
+    TRY(dev_alloc(h, &P.cfl, (size_t)nc));
+    TRY(dev_alloc(h, &P.ctau, (size_t)nc));
+    TRY(dev_alloc(h, &P.flag, (size_t)nc));
+    TRY(dev_alloc(h, &h->err, 4));
+    P.err = h->err;
+    int cap = 1;
+    while (cap < nc) cap <<= 1;
+    P.lim_cap = cap;
+    TRY(dev_alloc(h, &P.lim_list, (size_t)cap));
+    TRY(dev_alloc(h, &h->Ua, (size_t)nc_ex));
+    TRY(dev_alloc(h, &h->Ub, (size_t)nc_ex));
+    TRY(dev_alloc(h, &h->W, (size_t)nc_ex));
+    TRY(dev_alloc(h, &h->G, 2 * (size_t)nc_ex));
+    TRY(dev_alloc(h, &h->F, (size_t)ne));
+    for (int i = 0; i < 6; i++) TRY(dev_alloc(h, &h->io[i], (size_t)nc));
+    TRY(dev_alloc(h, &h->tau_bits, 1));
+    cudaMemset(h->err, 0, 4 * sizeof(int));
+    cudaMemset(P.flag, 0, (size_t)(nc ? nc : 1) * sizeof(unsigned int));
+    cudaMemset(h->Ua, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
+    cudaMemset(h->Ub, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
+    cudaMemset(h->W, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
+    cudaMemset(h->G, 0, 2 * (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
+    cudaMemset(P.cfl, 0, (size_t)(nc ? nc : 1) * sizeof(double));
+    cudaMemset(P.ctau, 0, (size_t)(nc ? nc : 1) * sizeof(double));
+    if (halo && halo->nranks > 1) {
+        std::string herr;
+        h->halo = halo_create(halo, nc, nc_ex, device, &herr);
+        if (!h->halo) { g_create_error = herr; cfd2d_fvm_destroy(h); return CFD2D_ENCCL; }
+        h->use_graph = false;   // NCCL point-to-point is enqueued directly
+    }
+    CUDA_TRY(h, cudaDeviceSynchronize());
+#undef TRY
+    *out = h;
+    return CFD2D_OK;
+}
+
+void cfd2d_fvm_destroy(cfd2d_fvm* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_graph(h);
+    if (h->halo) halo_destroy(h->halo);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int cfd2d_fvm_set_stream(cfd2d_fvm* h, void* s) {
+    if (!h) return CFD2D_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    drop_graph(h);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)s;
+    h->own_stream = false;
+    return 0;
+}
+
+int cfd2d_fvm_use_graph(cfd2d_fvm* h, int on) {
+    if (!h) return CFD2D_EINVAL;
+    h->use_graph = on && !h->halo;
+    if (!h->use_graph) drop_graph(h);
+    return 0;
+}
+
+int cfd2d_fvm_set_state(cfd2d_fvm* h, const double* ro, const double* ru, const double* rv, const double* re,
+                        const uint32_t* flag) {
+    if (!h || !ro || !ru || !rv || !re) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    size_t n = (size_t)h->nc * sizeof(double);
+    const double* src[4] = {ro, ru, rv, re};
+    for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaMemcpyAsync(h->io[i], src[i], n, cudaMemcpyHostToDevice, h->stream));
+    if (flag) CUDA_TRY(h, cudaMemcpyAsync(h->P.flag, flag, (size_t)h->nc * 4, cudaMemcpyHostToDevice, h->stream));
+    else CUDA_TRY(h, cudaMemsetAsync(h->P.flag, 0, (size_t)(h->nc ? h->nc : 1) * 4, h->stream));
+    if (h->nc) {
+        h->launches++;
+        k_pack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->io[0], h->io[1], h->io[2], h->io[3], h->Ua);
+    }
+    launch_prim(h, h->Ua, 0, h->nc);
+    int rc = exchange_U(h, h->Ua);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int cfd2d_fvm_calc_time_step(cfd2d_fvm* h, double* tau_out) {
+    if (!h) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->ctrl.steady) {
+        launch_tau_steady(h);
+    } else {
+        unsigned long long bits;
+        memcpy(&bits, &h->TAU, 8);
+        CUDA_TRY(h, cudaMemcpyAsync(h->tau_bits, &bits, 8, cudaMemcpyHostToDevice, h->stream));
+        if (h->nc) {
+            h->launches++;
+            k_tau_min<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->W, h->tau_bits);
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(&bits, h->tau_bits, 8, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        double tau;
+        memcpy(&tau, &bits, 8);
+        if (h->halo) {
+            int rc = halo_allreduce_min(h->halo, &tau, h->stream);   // MPI_Allreduce(MIN) analogue (fem_rkdg.cpp:413)
+            if (rc) { h->error = halo_error(h->halo); return rc; }
+        }
+        h->TAU = tau;
+        if (h->nc) {
+            h->launches++;
+            k_tau_fill<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, tau);
+        }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    if (tau_out) *tau_out = h->TAU;
+    return 0;
+}
+
+int cfd2d_fvm_step_async(cfd2d_fvm* h, int nsteps) {
+    if (!h || nsteps < 0) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (h->use_graph && !h->profiling) {
+        if (!h->graph_exec) {
+            int64_t l0 = h->launches;
+            CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            int rc = enqueue_step(h);
+            cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
+            h->launches = l0;
+            if (rc) return rc;
+            CUDA_TRY(h, e);
+            CUDA_TRY(h, cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
+        }
+        int per_step = 3 + 2 * (h->ctrl.order == 2 ? 2 : 1) + (h->ctrl.steady ? 1 : 0);
+        for (int s = 0; s < nsteps; s++) {
+            CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
+            h->launches += per_step;
+        }
+    } else {
+        for (int s = 0; s < nsteps; s++) {
+            int rc = enqueue_step(h);
+            if (rc) return rc;
+        }
+    }
+    if (!h->ctrl.steady) for (int s = 0; s < nsteps; s++) h->t += h->TAU;   // t += TAU, fvm_tvd.cpp:313
+    return 0;
+}
+
+int cfd2d_fvm_sync(cfd2d_fvm* h) {
+    if (!h) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return check_device_errors(h);
+}
+
+int cfd2d_fvm_step(cfd2d_fvm* h, int nsteps) {
+    int rc = cfd2d_fvm_step_async(h, nsteps);
+    if (rc) return rc;
+    return cfd2d_fvm_sync(h);
+}
+
+int cfd2d_fvm_get_state(cfd2d_fvm* h, double* ro, double* ru, double* rv, double* re, double* cTau, uint32_t* flag) {
+    if (!h || !ro || !ru || !rv || !re) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    size_t n = (size_t)h->nc * sizeof(double);
+    if (h->nc) {
+        h->launches++;
+        k_unpack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->Ua, h->io[0], h->io[1], h->io[2], h->io[3]);
+    }
+    double* dst[4] = {ro, ru, rv, re};
+    for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaMemcpyAsync(dst[i], h->io[i], n, cudaMemcpyDeviceToHost, h->stream));
+    if (cTau) CUDA_TRY(h, cudaMemcpyAsync(cTau, h->P.ctau, n, cudaMemcpyDeviceToHost, h->stream));
+    if (flag) CUDA_TRY(h, cudaMemcpyAsync(flag, h->P.flag, (size_t)h->nc * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int cfd2d_fvm_get_primitive(cfd2d_fvm* h, double* r, double* p, double* T, double* u, double* v, double* cz) {
+    if (!h) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    double* dst[6] = {r, p, T, u, v, cz};
+    double* dev[6];
+    for (int i = 0; i < 6; i++) dev[i] = dst[i] ? h->io[i] : nullptr;
+    if (h->nc) {
+        h->launches++;
+        k_primitive_out<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->Ua, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5]);
+    }
+    for (int i = 0; i < 6; i++)
+        if (dst[i]) CUDA_TRY(h, cudaMemcpyAsync(dst[i], h->io[i], (size_t)h->nc * 8, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+double cfd2d_fvm_tau(const cfd2d_fvm* h) { return h ? h->TAU : 0.0; }
+double cfd2d_fvm_time(const cfd2d_fvm* h) { return h ? h->t : 0.0; }
+int64_t cfd2d_fvm_launch_count(const cfd2d_fvm* h) { return h ? h->launches : 0; }
+
+int cfd2d_fvm_calc_grad(cfd2d_fvm* h, double* grad8) {
+    if (!h || !grad8) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    launch_grad(h);
+    double* tmp = nullptr;
+    CUDA_TRY(h, cudaMalloc(&tmp, (size_t)(h->nc ? h->nc : 1) * 64));
+    if (h->nc) k_unpack_grad<<<nblk(2 * (long long)h->nc, 256), 256, 0, h->stream>>>(h->nc, h->G, tmp);
+    cudaError_t e = cudaMemcpyAsync(grad8, tmp, (size_t)h->nc * 64, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    CUDA_TRY(h, e);
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int cfd2d_fvm_edge_fluxes(cfd2d_fvm* h, double* flux4) {
+    if (!h || !flux4) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int rc;
+    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h))) return rc; }
+    launch_flux(h, h->Ua, 0);
+    CUDA_TRY(h, cudaMemcpyAsync(flux4, h->F, (size_t)h->ne * 32, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    CUDA_TRY(h, cudaGetLastError());
+    return check_device_errors(h);
+}
+
+int cfd2d_fvm_profile(cfd2d_fvm* h, int nsteps, double* ms, int64_t* launches) {
+    if (!h || nsteps < 0) return CFD2D_EINVAL;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < CFD2D_NKERNELS; i++) { h->prof_ms[i] = 0; h->prof_n[i] = 0; }
+    h->profiling = true;
+    int rc = cfd2d_fvm_step_async(h, nsteps);
+    h->profiling = false;
+    if (rc) return rc;
+    rc = cfd2d_fvm_sync(h);
+    for (int i = 0; i < CFD2D_NKERNELS; i++) {
+        if (ms) ms[i] = h->prof_ms[i];
+        if (launches) launches[i] = h->prof_n[i];
+    }
+    return rc;
+}
+
+// ---- function-level known-answer entry points ---------------------------------------------------
+int cfd2d_kat_rim_orig(int device, int n, const double* in8, double gam, int max_newton, double* out5, int32_t* iters) {
+    g_create_error.clear();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); g_create_error = "no usable CUDA device"; return CFD2D_ENODEV; }
+    if (n <= 0) return 0;
+    if (max_newton <= 0) max_newton = 1000;
+    cfd2d_fvm* none = nullptr;
+    CUDA_TRY(none, cudaSetDevice(device));
+    double *din = nullptr, *dout = nullptr; int* dit = nullptr;
+    CUDA_TRY(none, cudaMalloc(&din, (size_t)n * 64));
+    CUDA_TRY(none, cudaMalloc(&dout, (size_t)n * 40));
+    CUDA_TRY(none, cudaMalloc(&dit, (size_t)n * 4));
+    CUDA_TRY(none, cudaMemcpy(din, in8, (size_t)n * 64, cudaMemcpyHostToDevice));
+    k_kat_rim<<<nblk(n, 128), 128>>>(make_rim(gam), max_newton, n, din, dout, dit);
+    CUDA_TRY(none, cudaDeviceSynchronize());
+    CUDA_TRY(none, cudaMemcpy(out5, dout, (size_t)n * 40, cudaMemcpyDeviceToHost));
+    std::vector<int> it(n);
+    CUDA_TRY(none, cudaMemcpy(it.data(), dit, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(din); cudaFree(dout); cudaFree(dit);
+    int bad = 0;
+    for (int i = 0; i < n; i++) { if (iters) iters[i] = it[i]; if (it[i] < 0) bad = CFD2D_ENEWTON; }
+    return bad;
+}
+
+int cfd2d_kat_calc_flux(int device, int n, const double* in12, double gam, int flux, double* out4) {
+    g_create_error.clear();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); g_create_error = "no usable CUDA device"; return CFD2D_ENODEV; }
+    if (n <= 0) return 0;
+    cfd2d_fvm* none = nullptr;
+    CUDA_TRY(none, cudaSetDevice(device));
+    double *din = nullptr, *dout = nullptr;
+    CUDA_TRY(none, cudaMalloc(&din, (size_t)n * 96));
+    CUDA_TRY(none, cudaMalloc(&dout, (size_t)n * 32));
+    CUDA_TRY(none, cudaMemcpy(din, in12, (size_t)n * 96, cudaMemcpyHostToDevice));
+    k_kat_flux<<<nblk(n, 128), 128>>>(make_rim(gam), flux, n, din, dout);
+    CUDA_TRY(none, cudaDeviceSynchronize());
+    CUDA_TRY(none, cudaMemcpy(out4, dout, (size_t)n * 32, cudaMemcpyDeviceToHost));
+    cudaFree(din); cudaFree(dout);
+    return 0;
+}
+
+}  // extern "C"

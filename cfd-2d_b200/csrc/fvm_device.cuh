@@ -1,0 +1,225 @@
+// fvm_device.cuh -- device-side physics of the FVM_TVD path (FP64, sm_100a).
+//
+// Every function states the reference code whose arithmetic it reproduces.  The whole library is
+// compiled with -fmad=false: the reference x86-64 build has no FMA contraction, and +,-,*,/,sqrt
+// are IEEE-exact on both sides, so apart from exp/log (<= 1 ulp on both, not identical) results
+// agree bit for bit.  Expressions keep the reference's left-to-right association.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CFD2D_GR 8.314472   // Material::gR, reference src/global.cpp:6
+
+// Material constants derived once on the host with the reference's own expressions
+// (Material::URS, global.cpp:11-12: Cv = Cp - gR/M; gam = Cp/Cv).
+struct MatC { double M, Cv, gam, gm1; };
+
+// Constants of rim_orig (global.cpp:235-249) for the fixed GAM = 1.4 the flux loop passes
+// (fvm_tvd.cpp:345,398).  Pure functions of GAM, evaluated on the host by the same expressions.
+struct RimC {
+    double GAM, AGAM, DGAM, GGAM, HGAM, FGAM, OGAM, QGAM, PGAM, RGAM, SGAM, TGAM;
+    double IAGAM;   // (1/AGAM)            global.cpp:389,395
+    double DG1;     // (1+DGAM)            global.cpp:384,391
+    double DGGG;    // DGAM*GGAM           global.cpp:384,391
+};
+
+struct Prim { double r, p, u, v; };
+
+// FVM_TVD::convertConsToPar (fvm_tvd.cpp:803-813) + Material::URS mode 0 (global.cpp:15-18).
+// Only r,p,u,v are kept: reconstruct/calcFlux read nothing else of an inner state.
+__device__ __forceinline__ Prim cons_to_prim(double ro, double ru, double rv, double re, double gm1) {
+    Prim w;
+    w.r = ro;
+    w.u = ru / ro;
+    w.v = rv / ro;
+    double E = re / ro;
+    double e = E - 0.5 * (w.u * w.u + w.v * w.v);
+    w.p = w.r * e * gm1;
+    return w;
+}
+
+// T as convertConsToPar leaves it: URS(1) after URS(0): e = p/(r*(gam-1)); T = e/Cv (global.cpp:20-23)
+__device__ __forceinline__ double prim_T(const Prim& w, const MatC& m) {
+    double e = w.p / (w.r * m.gm1);
+    return e / m.Cv;
+}
+
+// cz of URS(0): sqrt(gam*p/r) (global.cpp:17)
+__device__ __forceinline__ double prim_cz(const Prim& w, const MatC& m) { return sqrt(m.gam * w.p / w.r); }
+
+// FVM_TVD::boundaryCond (fvm_tvd.cpp:694-711) with CFDBnd{Inlet,Outlet,WallSlip}::run
+// (bnd_cond.cpp:75-110).  pL = (possibly extrapolated) r,p,u,v; TL = the CELL-CENTRE temperature
+// (reconstruct never updates T: SURVEY Q3).  Returns the ghost r,p,u,v and, for the LF flux, E.
+__device__ __forceinline__ Prim ghost_state(const Prim& pL, double TL, int kind, const double* __restrict__ par,
+                                            double nx, double ny, const MatC& m, double* E_out) {
+    Prim pR;
+    double T;
+    if (kind == 1) {            // CFDBndInlet
+        pR.u = par[0]; pR.v = par[1]; T = par[2]; pR.p = par[3];
+    } else if (kind == 2) {     // CFDBndOutlet
+        pR.u = pL.u; pR.v = pL.v; T = TL; pR.p = pL.p;
+    } else {                    // CFDBndWallSlip (and "no-slip")
+        double Un = pL.u * nx + pL.v * ny;
+        double Vx = nx * Un * 2.0;
+        double Vy = ny * Un * 2.0;
+        pR.u = pL.u - Vx; pR.v = pL.v - Vy; T = TL; pR.p = pL.p;
+    }
+    pR.r = pR.p * m.M / (T * CFD2D_GR);               // URS(2), global.cpp:26
+    if (E_out) {
+        double e = pR.p / (pR.r * m.gm1);             // URS(1), global.cpp:21
+        *E_out = e + 0.5 * (pR.u * pR.u + pR.v * pR.v); // fvm_tvd.cpp:703
+    }
+    return pR;
+}
+
+// One side of the Newton function of rim_orig (global.cpp:281-304): given the trial pressure P
+// returns F and its derivative FS for the side with state (PS, CS, RCS).
+__device__ __forceinline__ void rim_side(const RimC& k, double P, double PS, double CS, double RCS,
+                                         double& F, double& FS) {
+    double PP = P / PS;
+    if (PS > P) {                                  // rarefaction: lbl1 / lbl3
+        double ZF = CS * exp(log(PP) * k.OGAM);
+        F = k.DGAM * (ZF - CS);
+        FS = ZF / (k.GAM * P);
+    } else {                                       // shock
+        double PK = k.PGAM * PP + k.OGAM;
+        double ZN = RCS * sqrt(PK);
+        F = (P - PS) / ZN;
+        FS = (k.QGAM * PP + k.FGAM) / (k.RGAM * ZN * PK);
+    }
+}
+
+// rim_orig (global.cpp:232-405) with WB = WE = 0.  Quantities the reference computes but never
+// reads on the taken path (e.g. ZFB on a shock side, global.cpp:315) are skipped; every value that
+// is used is formed by the reference's own expression.  Returns the Newton iteration count, or -1
+// if `max_newton` was reached (the reference has no cap and would hang).
+__device__ __forceinline__ int rim_orig_dev(const RimC& k, int max_newton,
+                                            double RB, double PB, double UB, double VB,
+                                            double RE, double PE, double UE, double VE,
+                                            double& RI, double& EI, double& PI, double& UI, double& VI) {
+    const double eps = 1.0e-5;
+    double CB = sqrt(k.GAM * PB / RB);
+    double CE = sqrt(k.GAM * PE / RE);
+    double EB = CB * CB / k.SGAM;
+    double EE = CE * CE / k.SGAM;
+    double RCB = RB * CB;
+    double RCE = RE * CE;
+    double DU = UB - UE;
+    double US = 0.0, UF = 0.0, RF = 0.0, RS = 0.0, EF = 0.0, ES = 0.0;
+    double SBL, SFL, SSL, SEL;
+    int it = 0;
+    if (DU < -2.0 * (CB + CE) / k.AGAM) {          // vacuum, global.cpp:265-276
+        SBL = UB - CB;
+        SFL = UB + 2.0 * CB / k.AGAM;
+        SSL = UE - 2.0 * CE / k.AGAM;
+        SEL = UE + CE;
+    } else {
+        double P = (PB * RCE + PE * RCB + DU * RCB * RCE) / (RCB + RCE);   // global.cpp:277
+        for (;;) {
+            if (P < eps) P = eps;
+            double F1, FS1, F2, FS2;
+            rim_side(k, P, PB, CB, RCB, F1, FS1);
+            rim_side(k, P, PE, CE, RCE, F2, FS2);
+            double res = DU - F1 - F2;
+            double DP = res / (FS1 + FS2);
+            P = P + DP;
+            ++it;
+            if (!(fabs(res) > eps)) break;
+            if (it >= max_newton) { it = -1; break; }
+        }
+        double PPB = P / PB;
+        double PPE = P / PE;
+        if (PB > P) {                              // lbl6: left rarefaction
+            double ZFB = CB * exp(log(PPB) * k.OGAM);
+            EF = ZFB * ZFB / k.SGAM;
+            UF = UB + k.DGAM * (CB - ZFB);
+            RF = P / (k.AGAM * EF);
+            SBL = UB - CB;
+            SFL = UF - ZFB;
+        } else {                                   // left shock
+            double D = UB - sqrt((k.TGAM * P + k.HGAM * PB) / RB);
+            double UBD = UB - D;
+            double RUBD = RB * UBD;
+            RF = RUBD * RUBD / (PB - P + RUBD * UBD);
+            UF = D + RUBD / RF;
+            EF = P / (k.AGAM * RF);
+            SBL = D;
+            SFL = D;
+        }
+        if (PE > P) {                              // lbl8: right rarefaction
+            double ZFE = CE * exp(log(PPE) * k.OGAM);
+            ES = ZFE * ZFE / k.SGAM;
+            US = UE - k.DGAM * (CE - ZFE);
+            RS = P / (k.AGAM * ES);
+            SSL = US + ZFE;
+            SEL = UE + CE;
+        } else {                                   // right shock
+            double D = UE + sqrt((k.TGAM * P + k.HGAM * PE) / RE);
+            double UED = UE - D;
+            double RUED = RE * UED;
+            RS = RUED * RUED / (PE - P + RUED * UED);
+            US = D + RUED / RS;
+            ES = P / (k.AGAM * RS);
+            SEL = D;
+            SSL = D;
+        }
+    }
+    // sampling at x/t = 0, global.cpp:353-400
+    if (SEL <= 0.0) {
+        RI = RE; EI = EE; UI = UE; VI = VE;
+    } else if (SBL >= 0.0) {
+        RI = RB; EI = EB; UI = UB; VI = VB;
+    } else if ((SSL >= 0.0) && (SFL <= 0.0)) {
+        if (US >= 0.0) { RI = RF; EI = EF; UI = UF; VI = VB; }
+        else           { RI = RS; EI = ES; UI = US; VI = VE; }
+    } else if (SFL > 0.0) {
+        UI = (UB + k.DGGG * sqrt(EB)) / k.DG1;
+        VI = VB;
+        EI = (UI * UI) / k.SGAM;
+        RI = RB * exp(log(EI / EB) * k.IAGAM);
+    } else {
+        UI = (UE - k.DGGG * sqrt(EE)) / k.DG1;
+        VI = VE;
+        EI = (UI * UI) / k.SGAM;
+        RI = RE * exp(log(EI / EE) * k.IAGAM);
+    }
+    PI = k.AGAM * EI * RI;
+    return it;
+}
+
+// FVM_TVD::calcFlux, Godunov block (fvm_tvd.cpp:604-622).
+__device__ __forceinline__ int flux_godunov_dev(const RimC& k, int max_newton, const Prim& L, const Prim& R,
+                                                double nx, double ny, double& fr, double& fu, double& fv, double& fe) {
+    double unl = L.u * nx + L.v * ny;
+    double unr = R.u * nx + R.v * ny;
+    double utl = L.u * ny - L.v * nx;
+    double utr = R.u * ny - R.v * nx;
+    double RI, EI, PI, UN, UT;
+    int it = rim_orig_dev(k, max_newton, L.r, L.p, unl, utl, R.r, R.p, unr, utr, RI, EI, PI, UN, UT);
+    double UI = UN * nx + UT * ny;
+    double VI = UN * ny - UT * nx;
+    fr = RI * UN;
+    fu = fr * UI + PI * nx;
+    fv = fr * VI + PI * ny;
+    fe = (RI * (EI + 0.5 * (UI * UI + VI * VI)) + PI) * UN;
+    return it;
+}
+
+// The commented Lax-Friedrichs block of FVM_TVD::calcFlux (fvm_tvd.cpp:623-642); EL/ER are the
+// total specific energies pL.E / pR.E (cell-centre value on an inner side, ghost value on a boundary).
+__device__ __forceinline__ void flux_lax_dev(double GAM, const Prim& L, double EL, const Prim& R, double ER,
+                                             double nx, double ny, double& fr, double& fu, double& fv, double& fe) {
+    double unl = L.u * nx + L.v * ny;
+    double unr = R.u * nx + R.v * ny;
+    double al = fabs(unl) + sqrt(GAM * L.p / L.r);
+    double ar = fabs(unr) + sqrt(GAM * R.p / R.r);
+    double alpha = (al > ar) ? al : ar;            // _max_, grid.h:102
+    double rol = L.r, rul = L.r * L.u, rvl = L.r * L.v, rel = L.r * EL;
+    double ror = R.r, rur = R.r * R.u, rvr = R.r * R.v, rer = R.r * ER;
+    double frl = rol * unl;
+    double frr = ror * unr;
+    fr = 0.5 * (frr + frl - alpha * (ror - rol));
+    fu = 0.5 * (frr * R.u + frl * L.u + (R.p + L.p) * nx - alpha * (rur - rul));
+    fv = 0.5 * (frr * R.v + frl * L.v + (R.p + L.p) * ny - alpha * (rvr - rvl));
+    fe = 0.5 * ((rer + R.p) * unr + (rel + L.p) * unl - alpha * (rer - rel));
+}

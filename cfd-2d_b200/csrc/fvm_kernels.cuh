@@ -1,0 +1,426 @@
+// fvm_kernels.cuh -- the CUDA kernels of the FVM_TVD path (sm_100a, FP64, HBM-bound gathers).
+//
+// Data layout in HBM: 32-byte records, one DRAM sector each, so that an
+// indirect (neighbour) read costs exactly one sector:
+//   U4[c] = {ro, ru, rv, re}                 conservative state (two buffers: Ua = step start /
+//                                            result, Ub = after RK stage 1)
+//   W4[c] = {r, p, u, v}                     primitive cache, written by the update kernels
+//   G8[c] = {Rx,Ry,Px,Py, Ux,Uy,Vx,Vy}       Green-Gauss gradients (two sectors)
+//   F4[e] = {fr,fu,fv,fe} * (l/2)            edge flux staging
+// plus SoA per-slot / per-edge geometry read fully coalesced.
+#pragma once
+#include "fvm_device.cuh"
+
+struct KParams {
+    int nc, nc_ex, ne, nmat;
+    int order, flux, max_newton, steady;
+    double CFL;
+    double lim[5];
+    RimC rim;
+    // tables
+    const MatC* mat;        // [nmat]
+    const int* bc_kind;     // [nbc]
+    const double* bc_par;   // [4*nbc]
+    const unsigned char* cell_mat; // [nc_ex]
+    // per (cell, slot) gather tables, slot-major [3][nc]
+    const int* s_nb;        // neighbour cell, or -1-bc on a boundary edge
+    const double* s_nx;     // outward normal = sign * Edge::n
+    const double* s_ny;
+    const double* s_l;      // Edge::l
+    const int* s_es;        // edge*2 + (cell is c2)
+    const double* cell_S;   // [nc_ex]
+    // per edge
+    const int2* e_c;        // {c1, c2}
+    const double2* e_n;     // Edge::n
+    const double* e_l2;     // Edge::l * 0.5
+    const double4* e_d1;    // Gauss points relative to c1's centre {g1x-cx,g1y-cy,g2x-cx,g2y-cy}
+    const double4* e_d2;    // same for c2 (unused on boundary edges)
+    const int* e_bc;
+    // state
+    double* cfl;            // cTau/S per owned cell
+    double* ctau;           // cTau
+    unsigned int* flag;
+    int* err;               // [0] Newton-cap hits  [1] flagged-cell count  [2] Newton iterations (KAT)
+    int* lim_list;          // compacted flagged cells (unordered until sorted)
+    int lim_cap;                         // power of two >= nc
+};
+
+__device__ __forceinline__ double4 ld4(const double4* __restrict__ p, int i) {
+    // two 16-byte loads of one 32-byte sector
+    const double2* q = reinterpret_cast<const double2*>(p + i);
+    double2 a = __ldg(q), b = __ldg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ double4 ld4cg(const double4* p, int i) {
+    const double2* q = reinterpret_cast<const double2*>(p + i);
+    double2 a = __ldcg(q), b = __ldcg(q + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void st4(double4* p, int i, double4 v) {
+    double2* q = reinterpret_cast<double2*>(p + i);
+    q[0] = make_double2(v.x, v.y);
+    q[1] = make_double2(v.z, v.w);
+}
+
+__device__ __forceinline__ MatC get_mat(const KParams& P, int c) {
+    int im = (P.nmat > 1) ? (int)P.cell_mat[c] : 0;
+    return P.mat[im];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K0: U4 -> W4 for cells [c0, c1)  (FVM_TVD::convertConsToPar, fvm_tvd.cpp:803-813)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_prim(KParams P, const double4* __restrict__ U, double4* __restrict__ W, int c0, int c1) {
+    int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c1) return;
+    double4 u = ld4cg(U, c);
+    MatC m = get_mat(P, c);
+    Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
+    st4(W, c, make_double4(w.r, w.p, w.u, w.v));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1: time step (FVM_TVD::calcTimeStep, fvm_tvd.cpp:216-240).
+//   steady:   cTau[c] = CFL*S/max(|u|+cz,|v|+cz), cfl[c] = cTau/S
+//   unsteady: block/warp-shuffle min of the same quantity -> atomicMin on the (positive) double's
+//             bit pattern; min is order independent => bit-safe
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cell_tau(const KParams& P, const double4& w4, int c) {
+    MatC m = get_mat(P, c);
+    Prim w = {w4.x, w4.y, w4.z, w4.w};
+    double cz = prim_cz(w, m);
+    double a = fabs(w.u) + cz, b = fabs(w.v) + cz;
+    double mx = (a > b) ? a : b;
+    return P.CFL * P.cell_S[c] / mx;
+}
+
+__global__ void __launch_bounds__(256) k_tau_steady(KParams P, const double4* __restrict__ W) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nc) return;
+    double t = cell_tau(P, ld4cg(W, c), c);
+    P.ctau[c] = t;
+    P.cfl[c] = t / P.cell_S[c];
+}
+
+__global__ void __launch_bounds__(256) k_tau_min(KParams P, const double4* __restrict__ W, unsigned long long* __restrict__ out_bits) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    double t = __longlong_as_double(0x7ff0000000000000LL);  // +inf
+    if (c < P.nc) t = cell_tau(P, ld4cg(W, c), c);
+    // the reference's "if (TAU > x) TAU = x" ignores NaN candidates; so does fmin
+    for (int o = 16; o > 0; o >>= 1) t = fmin(t, __shfl_xor_sync(0xffffffffu, t, o));
+    __shared__ double sm[8];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sm[w] = t;
+    __syncthreads();
+    if (w == 0) {
+        t = (l < 8) ? sm[l] : __longlong_as_double(0x7ff0000000000000LL);
+        for (int o = 4; o > 0; o >>= 1) t = fmin(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (l == 0 && t > 0.0) atomicMin(out_bits, (unsigned long long)__double_as_longlong(t));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_tau_fill(KParams P, double tau) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nc) return;
+    P.ctau[c] = tau;
+    P.cfl[c] = tau / P.cell_S[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: boundary ghost state + Green-Gauss gradient GATHER (FVM_TVD::calcGrad, fvm_tvd.cpp:242-301;
+// boundaryCond :694-711).  One thread per owned cell; the three edge terms are added in the cell's
+// edgesInd (= ascending edge id) order, each formed exactly as the reference's edge loop forms it
+// -- ((pL+pR)/2 * n.x) * l with the edge's own normal, "+=" on the c1 side and "-=" on the c2 side
+// (the outward normal s*n reproduces the sign exactly) -- then the true division by S.  No atomics.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nc) return;
+    double4 ws = ld4(W, c);
+    double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int nb = __ldg(P.s_nb + (size_t)k * P.nc + c);
+        double nx = __ldg(P.s_nx + (size_t)k * P.nc + c);
+        double ny = __ldg(P.s_ny + (size_t)k * P.nc + c);
+        double l = __ldg(P.s_l + (size_t)k * P.nc + c);
+        double4 wn;
+        if (nb >= 0) {
+            wn = ld4(W, nb);
+        } else {
+            int ib = -1 - nb;
+            MatC m = get_mat(P, c);
+            Prim pL = {ws.x, ws.y, ws.z, ws.w};
+            Prim pR = ghost_state(pL, prim_T(pL, m), P.bc_kind[ib], P.bc_par + 4 * ib, nx, ny, m, nullptr);
+            wn = make_double4(pR.r, pR.p, pR.u, pR.v);
+        }
+        double tr = (ws.x + wn.x) / 2, tp = (ws.y + wn.y) / 2, tu = (ws.z + wn.z) / 2, tv = (ws.w + wn.w) / 2;
+        g[0] += tr * nx * l; g[1] += tr * ny * l;
+        g[2] += tp * nx * l; g[3] += tp * ny * l;
+        g[4] += tu * nx * l; g[5] += tu * ny * l;
+        g[6] += tv * nx * l; g[7] += tv * ny * l;
+    }
+    double si = P.cell_S[c];
+    st4(G, 2 * c, make_double4(g[0] / si, g[1] / si, g[2] / si, g[3] / si));
+    st4(G, 2 * c + 1, make_double4(g[4] / si, g[5] / si, g[6] / si, g[7] / si));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: per-edge linear reconstruction at the two Gauss points + numerical flux
+// (FVM_TVD::reconstruct fvm_tvd.cpp:646-691, calcFlux :602-643, rim_orig global.cpp:232-405, the
+// Gauss-point loop of run() :341-352).  Writes F4[e] = (sum over GPs) * (l*0.5), the quantity the
+// reference scatters (:353-363).  FLUX: 0 Godunov, 1 Lax-Friedrichs.  ORDER: 2 linear, 1 constant.
+// ---------------------------------------------------------------------------------------------
+template <int FLUX, int ORDER>
+__global__ void __launch_bounds__(128) k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
+                                              const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2) {
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= P.ne) return;
+    int2 cc = __ldg(P.e_c + e);
+    double2 n = __ldg(P.e_n + e);
+    double4 w1 = ld4(W, cc.x);
+    Prim c1 = {w1.x, w1.y, w1.z, w1.w};
+    Prim c2 = c1;
+    double E1 = 0.0, E2 = 0.0;
+    double4 d1 = make_double4(0, 0, 0, 0), d2 = d1, ga1 = d1, gb1 = d1, ga2 = d1, gb2 = d1;
+    if (ORDER == 2) {
+        d1 = ld4(P.e_d1, e);
+        ga1 = ld4(G, 2 * cc.x);
+        gb1 = ld4(G, 2 * cc.x + 1);
+    }
+    if (FLUX == 1) { double4 u = ld4(Ucur, cc.x); E1 = u.w / u.x; }
+    const bool inner = cc.y >= 0;
+    MatC m; double T1 = 0.0; int kind = 0; const double* par = nullptr;
+    if (inner) {
+        double4 w2 = ld4(W, cc.y);
+        c2.r = w2.x; c2.p = w2.y; c2.u = w2.z; c2.v = w2.w;
+        if (ORDER == 2) {
+            d2 = ld4(P.e_d2, e);
+            ga2 = ld4(G, 2 * cc.y);
+            gb2 = ld4(G, 2 * cc.y + 1);
+        }
+        if (FLUX == 1) { double4 u = ld4(Ucur, cc.y); E2 = u.w / u.x; }
+    } else {
+        m = get_mat(P, cc.x);
+        T1 = prim_T(c1, m);
+        int ib = __ldg(P.e_bc + e);
+        kind = P.bc_kind[ib];
+        par = P.bc_par + 4 * ib;
+    }
+    double fr = 0.0, fu = 0.0, fv = 0.0, fe = 0.0;
+    int bad = 0;
+#pragma unroll
+    for (int gp = 0; gp < 2; gp++) {
+        Prim L = c1, R = c2;
+        double ER = E2;
+        if (ORDER == 2) {
+            double dx = gp ? d1.z : d1.x, dy = gp ? d1.w : d1.y;
+            L.r += ga1.x * dx + ga1.y * dy;
+            L.p += ga1.z * dx + ga1.w * dy;
+            L.u += gb1.x * dx + gb1.y * dy;
+            L.v += gb1.z * dx + gb1.w * dy;
+        }
+        if (inner) {
+            if (ORDER == 2) {
+                double dx = gp ? d2.z : d2.x, dy = gp ? d2.w : d2.y;
+                R.r += ga2.x * dx + ga2.y * dy;
+                R.p += ga2.z * dx + ga2.w * dy;
+                R.u += gb2.x * dx + gb2.y * dy;
+                R.v += gb2.z * dx + gb2.w * dy;
+            }
+        } else {
+            R = ghost_state(L, T1, kind, par, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
+        }
+        double f0, f1, f2, f3;
+        if (FLUX == 0) {
+            int it = flux_godunov_dev(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
+            bad |= (it < 0);
+        } else {
+            flux_lax_dev(P.rim.GAM, L, E1, R, ER, n.x, n.y, f0, f1, f2, f3);
+        }
+        fr += f0; fu += f1; fv += f2; fe += f3;
+    }
+    if (bad) atomicAdd(P.err, 1);
+    if (scale_by_l2) {
+        double l2 = __ldg(P.e_l2 + e);
+        fr = fr * l2; fu = fu * l2; fv = fv * l2; fe = fe * l2;
+    }
+    st4(F, e, make_double4(fr, fu, fv, fe));
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4 / K5: deterministic residual GATHER + RK stage update, fused.
+//   reference: scatter R[c1] -= F*l2, R[c2] += F*l2 over ascending edges (fvm_tvd.cpp:353-363),
+//   then U += (cTau/S)*R for unflagged cells (:366-374); stage 2 additionally the half-sum with the
+//   old state and the limit tests (:430-447).  Here each cell sums its three staged edge fluxes in
+//   edgesInd (ascending id) order starting from 0.0 -- the same additions in the same order, so R is
+//   never stored and no float atomics are needed.  The new primitive cache W4 is written as well.
+// STAGE 1: Uout(=Ub) = Uin(=Ua) + cfl*R.     STAGE 2: Ua = 0.5*(Ua + (Ub + cfl*R)), flags.
+// ---------------------------------------------------------------------------------------------
+template <int STAGE>
+__global__ void __launch_bounds__(256) k_update(KParams P, const double4* __restrict__ F, const double4* Uin,
+                                                double4* Uout, double4* __restrict__ W) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nc) return;
+    unsigned int fl = P.flag[c];
+    if (fl & 2u) {                       // cellIsLim: frozen until remediated (:368, :421, :432)
+        if (STAGE == 1) st4(Uout, c, ld4cg(Uin, c));
+        else {
+            int pos = atomicAdd(P.err + 1, 1);
+            if (pos < P.lim_cap) P.lim_list[pos] = c;
+        }
+        return;
+    }
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        int es = __ldg(P.s_es + (size_t)k * P.nc + c);
+        double4 f = ld4cg(F, es >> 1);
+        if (es & 1) { r0 += f.x; r1 += f.y; r2 += f.z; r3 += f.w; }
+        else        { r0 -= f.x; r1 -= f.y; r2 -= f.z; r3 -= f.w; }
+    }
+    double cfl = P.cfl[c];
+    double4 u = ld4cg(Uin, c);
+    u.x += cfl * r0; u.y += cfl * r1; u.z += cfl * r2; u.w += cfl * r3;
+    MatC m = get_mat(P, c);
+    if (STAGE == 2) {
+        double4 uo = ld4cg(Uout, c);     // Ua: the state at step start (ro_old ...)
+        u.x = 0.5 * (uo.x + u.x); u.y = 0.5 * (uo.y + u.y); u.z = 0.5 * (uo.z + u.z); u.w = 0.5 * (uo.w + u.w);
+    }
+    Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
+    st4(Uout, c, u);
+    st4(W, c, make_double4(w.r, w.p, w.u, w.v));
+    if (STAGE == 2) {
+        bool lim = (w.r < P.lim[0]) | (w.r > P.lim[1]) | (w.p < P.lim[2]) | (w.p > P.lim[3]) |
+                   (fabs(w.u) > P.lim[4]) | (fabs(w.v) > P.lim[4]);
+        if (lim) {
+            P.flag[c] = fl | 2u;         // setCellFlagLim
+            int pos = atomicAdd(P.err + 1, 1);
+            if (pos < P.lim_cap) P.lim_list[pos] = c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: FVM_TVD::remediateLimCells (fvm_tvd.cpp:464-499).  Rare path.  One block: sort the flagged
+// list ascending (bitonic, in global memory), then thread 0 replays the reference's in-place,
+// ascending-cell-order sweep (the order matters when two flagged cells are neighbours).  Keeps the
+// reference's quirk: only edges[].c2 is averaged, i.e. the cell itself when it is the edge's c2.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_remediate(KParams P, double4* U, double4* W) {
+    int n = P.err[1];
+    if (n == 0) return;
+    if (n > P.lim_cap) n = P.lim_cap;
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    int* a = P.lim_list;
+    for (int i = n + threadIdx.x; i < np2; i += blockDim.x) a[i] = 0x7fffffff;
+    __syncthreads();
+    for (int k = 2; k <= np2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
+                int ixj = i ^ j;
+                if (ixj > i) {
+                    int x = a[i], y = a[ixj];
+                    bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (threadIdx.x == 0) {
+        for (int q = 0; q < n; q++) {
+            int c = a[q];
+            double sRO = 0.0, sRU = 0.0, sRV = 0.0, sRE = 0.0, S = 0.0;
+            for (int k = 0; k < 3; k++) {
+                int es = P.s_es[(size_t)k * P.nc + c];
+                int j = P.e_c[es >> 1].y;
+                if (j >= 0) {
+                    double s = P.cell_S[j];
+                    double4 u = U[j];
+                    S += s;
+                    sRO += u.x * s; sRU += u.y * s; sRV += u.z * s; sRE += u.w * s;
+                }
+            }
+            double4 u = make_double4(sRO / S, sRU / S, sRV / S, sRE / S);
+            U[c] = u;
+            MatC m = get_mat(P, c);
+            Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
+            W[c] = make_double4(w.r, w.p, w.u, w.v);
+            unsigned int fl = P.flag[c];
+            fl += 0x010000u;
+            if (fl & 0x200000u) fl &= 0x001110u;
+            P.flag[c] = fl;
+        }
+        P.err[1] = 0;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// state import/export: the reference's four separate arrays <-> U4 records
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack_state(int n, const double* __restrict__ ro, const double* __restrict__ ru,
+                                                    const double* __restrict__ rv, const double* __restrict__ re,
+                                                    double4* __restrict__ U) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    st4(U, c, make_double4(ro[c], ru[c], rv[c], re[c]));
+}
+
+__global__ void __launch_bounds__(256) k_unpack_state(int n, const double4* __restrict__ U, double* __restrict__ ro,
+                                                      double* __restrict__ ru, double* __restrict__ rv, double* __restrict__ re) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    double4 u = ld4cg(U, c);
+    ro[c] = u.x; ru[c] = u.y; rv[c] = u.z; re[c] = u.w;
+}
+
+// K8: primitive fields for FVM_TVD::save (convertConsToPar per cell, fvm_tvd.cpp:529-572)
+__global__ void __launch_bounds__(256) k_primitive_out(KParams P, const double4* __restrict__ U, double* r, double* p, double* T,
+                                                       double* u, double* v, double* cz) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nc) return;
+    double4 q = ld4cg(U, c);
+    MatC m = get_mat(P, c);
+    Prim w = cons_to_prim(q.x, q.y, q.z, q.w, m.gm1);
+    if (r) r[c] = w.r;
+    if (p) p[c] = w.p;
+    if (T) T[c] = prim_T(w, m);
+    if (u) u[c] = w.u;
+    if (v) v[c] = w.v;
+    if (cz) cz[c] = prim_cz(w, m);
+}
+
+__global__ void __launch_bounds__(256) k_unpack_grad(int n, const double4* __restrict__ G, double* __restrict__ out8) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * n) return;
+    double4 g = ld4cg(G, i);
+    out8[4 * (size_t)i + 0] = g.x; out8[4 * (size_t)i + 1] = g.y; out8[4 * (size_t)i + 2] = g.z; out8[4 * (size_t)i + 3] = g.w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// function-level known-answer kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_kat_rim(RimC rc, int max_newton, int n, const double* __restrict__ in8, double* __restrict__ out5, int* __restrict__ iters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* a = in8 + 8 * (size_t)i;
+    double RI, EI, PI, UI, VI;
+    int it = rim_orig_dev(rc, max_newton, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], RI, EI, PI, UI, VI);
+    double* q = out5 + 5 * (size_t)i;
+    q[0] = RI; q[1] = EI; q[2] = PI; q[3] = UI; q[4] = VI;
+    if (iters) iters[i] = it;
+}
+
+__global__ void k_kat_flux(RimC rc, int flux, int n, const double* __restrict__ in12, double* __restrict__ out4) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* a = in12 + 12 * (size_t)i;
+    Prim L = {a[0], a[1], a[2], a[3]}, R = {a[5], a[6], a[7], a[8]};
+    double f0, f1, f2, f3;
+    if (flux == 1) flux_lax_dev(rc.GAM, L, a[4], R, a[9], a[10], a[11], f0, f1, f2, f3);
+    else flux_godunov_dev(rc, 1000, L, R, a[10], a[11], f0, f1, f2, f3);
+    double* q = out4 + 4 * (size_t)i;
+    q[0] = f0; q[1] = f1; q[2] = f2; q[3] = f3;
+}

@@ -1,0 +1,21 @@
+// halo_nccl.h -- ghost-cell exchange of one rank over NCCL send/recv (NVLink 5 / NVSwitch).
+//
+// Replaces Method::exchange (reference src/methods/method.h:13-127, MPI_Send/MPI_Recv per peer in
+// rank order, global.cpp:607-659): one pack kernel gathers the send lists of ALL peers into a
+// staging buffer, then a single ncclGroup of ncclSend/ncclRecv; each peer's data lands contiguously
+// in the halo slice [nc + recvShift[p], ...) of the destination field, so no unpack is needed.
+// NCCL is dlopen()ed ("libnccl.so.2") so the single-GPU path has no NCCL dependency and a process
+// that already loaded the torch-bundled NCCL shares it.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include "../../include/cfd2d_fvm.h"
+
+struct HaloNccl;
+HaloNccl* halo_create(const cfd2d_halo* d, int nc, int nc_ex, int device, std::string* err);
+void halo_destroy(HaloNccl* h);
+// exchange records of rec4 double4's per cell (1: U4, 2: G8) of `field` ([nc_ex] records)
+int halo_exchange(HaloNccl* h, double4* field, int rec4, cudaStream_t s, int64_t* launches);
+int halo_allreduce_min(HaloNccl* h, double* v, cudaStream_t s);
+const char* halo_error(HaloNccl* h);

@@ -1,0 +1,63 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/cfd2d_fvm.h declares; the
+product path fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from cfd2d_b200 import cases, fvm
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    h = open(os.path.join(ROOT, "include", "cfd2d_fvm.h")).read()
+    h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
+    return sorted(set(re.findall(r"\b(cfd2d_[a-z0-9_]+)\s*\(", h)))
+
+
+def test_header_symbols_are_exported():
+    if not os.path.exists(fvm.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    lib = ctypes.CDLL(fvm.LIB_PATH)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cfd2d_fvm.h but not exported"
+    assert set(fvm.EXPORTS) <= set(names)
+
+
+def test_version_string():
+    lib = fvm.load_library()
+    assert b"sm_100a" in lib.cfd2d_version()
+
+
+def _gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+@pytest.mark.skipif(_gpu(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback_without_gpu():
+    c = cases.strip(4, 2)
+    with pytest.raises(fvm.CFDError) as e:
+        fvm.Solver(c.mesh, c.task)
+    assert e.value.code == -2          # CFD2D_ENODEV
+
+
+def test_create_rejects_bad_arguments():
+    c = cases.strip(4, 2)
+    with pytest.raises(fvm.CFDError) as e:
+        fvm.Solver(c.mesh, c.task, order=3)
+    assert e.value.code == -1
+    m = c.mesh
+    bad = np.array(m.edge_bc, copy=True)
+    bad[m.edge_c2 < 0] = -1
+    import dataclasses
+    m2 = dataclasses.replace(m, edge_bc=bad)
+    with pytest.raises(fvm.CFDError) as e:
+        fvm.Solver(m2, c.task)
+    assert e.value.code == -5          # CFD2D_EBC, fvm_tvd.cpp:706-710

@@ -1,0 +1,210 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI (ctypes), against
+  (1) the CPU oracle on the same seeded inputs, and
+  (2) the committed golden vectors produced by the REAL reference (tests/golden/).
+
+Tolerances.  +,-,*,/,sqrt are IEEE-exact on both sides and the library is built with -fmad=false,
+so everything that does not go through exp/log must be BIT-EXACT: gradients, ghost states, the
+Lax-Friedrichs variants, time step, flags.  The exact Riemann solver calls exp/log (CUDA: <= 1 ulp,
+glibc: <= 1 ulp, not identical), so the Godunov runs are held to the north-star tolerance:
+relative L-infinity <= 1e-12 per conservative variable (SURVEY.md section 8(c) norm).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as pc
+from cfd2d_b200 import cases, fvm
+from oracle import port as P
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-12
+
+
+def gold(name):
+    return np.load(os.path.join(G, name + ".npz"))
+
+
+def relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def test_kat_rim_orig_vs_oracle_and_golden():
+    a = pc.kat_rim_inputs()
+    got, it = fvm.kat_rim_orig(a)
+    ref, rit = P.rim_orig(a)
+    g = gold("kat_rim_orig")["out"]
+    assert np.array_equal(ref, g)
+    assert (it >= 0).all()
+    # Newton trip counts agree except where a last-bit exp/log difference flips the exit test
+    assert (it != rit).mean() < 1e-2
+    same = it == rit
+    scale = np.abs(g).max(axis=0)
+    err = (np.abs(got - g)[same] / scale).max()
+    assert err < 1e-13, err
+    # the vacuum branch and the pure-left/right sampling never touch exp/log: bit-exact there
+    vac = rit == 0
+    assert vac.sum() >= 50 and np.array_equal(got[vac], g[vac])
+
+
+def test_kat_newton_cap():
+    bad = np.array([[1.01565357, 21443.1360, -3000.0, -12.56, 0.190079326, 153029.532, 3000.0, 3.72]])
+    _, it = fvm.kat_rim_orig(bad, max_newton=50)
+    assert it[0] == -1
+
+
+def test_kat_calc_flux():
+    f = pc.kat_flux_inputs()
+    g = gold("kat_calc_flux")
+    lax = fvm.kat_calc_flux(f, flux=fvm.FLUX_LAX)
+    assert np.array_equal(lax, g["lax"])                  # sqrt only -> bit-exact
+    god = fvm.kat_calc_flux(f, flux=fvm.FLUX_GODUNOV)
+    scale = np.abs(g["godunov"]).max(axis=0)
+    assert (np.abs(god - g["godunov"]) / scale).max() < 1e-13
+
+
+@pytest.mark.parametrize("name", list(pc.CASES))
+def test_run_matches_reference_golden_and_oracle(name):
+    c, spec, st = pc.build(name)
+    g = gold(name)
+    exact = spec["flux"] == 1          # Lax-Friedrichs: no transcendental functions
+    s = fvm.Solver(c.mesh, c.task, spec["flux"], spec["order"])
+    s.set_state(*st)
+    tau = s.calc_time_step()
+    assert tau == float(g["tau"])
+    grad = s.calc_grad()
+    assert np.array_equal(grad, g["grad0"]), relerr(grad, g["grad0"])
+    flux = s.edge_fluxes()
+    if exact:
+        assert np.array_equal(flux, g["flux0"])
+    else:
+        assert (np.abs(flux - g["flux0"]) / np.abs(g["flux0"]).max(axis=0)).max() < 1e-13
+    n = int(g["nsteps"])
+    for tag, k in (("mid", n // 2), ("fin", n - n // 2)):
+        s.step(k)
+        ro, ru, rv, re, ct, fl = s.get_state()
+        ref = [g[f"{tag}_{q}"] for q in ("ro", "ru", "rv", "re")]
+        assert np.array_equal(fl, g[f"{tag}_flag"]), (name, tag, "flags")
+        assert np.array_equal(ct, g[f"{tag}_ctau"]) or spec.get("steady"), (name, tag, "cTau")
+        if exact:
+            for a, b in zip((ro, ru, rv, re), ref):
+                assert np.array_equal(a, b), (name, tag)
+        else:
+            e = pc.err_norm((ro, ru, rv, re), ref)
+            assert max(e) < TOL, (name, tag, e)
+            if spec.get("steady"):
+                assert relerr(ct, g[f"{tag}_ctau"]) < TOL
+    # and the oracle port agrees with the golden (checker sanity on this box)
+    o = P.OracleSolver(c.mesh, c.task, spec["flux"], spec["order"])
+    o.set_state(*st)
+    o.calc_time_step()
+    o.step(n)
+    assert np.array_equal(o.get_state()[0], g["fin_ro"])
+    o.close()
+    s.close()
+
+
+def test_graph_and_eager_paths_are_bit_identical():
+    c = cases.channel(48, 24, jitter=0.2, shuffle=True)
+    st = c.smooth_state()
+    outs = []
+    for graph in (True, False):
+        s = fvm.Solver(c.mesh, c.task)
+        s.use_graph(graph)
+        s.set_state(*st)
+        s.calc_time_step()
+        s.step(7)
+        s.step(3)
+        outs.append(s.get_state())
+        s.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
+def test_run_to_run_determinism():
+    c = cases.channel(64, 32, jitter=0.2, shuffle=True)
+    st = c.smooth_state()
+    res = []
+    for _ in range(2):
+        s = fvm.Solver(c.mesh, c.task)
+        s.set_state(*st)
+        s.calc_time_step()
+        s.step(20)
+        res.append(s.get_state())
+        s.close()
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)          # gather, no float atomics
+
+
+def test_medium_mesh_vs_oracle():
+    """~46k cells (the oracle finishes in seconds): parity at a size where the grid is many waves."""
+    c = cases.channel(240, 96, jitter=0.2)
+    st = c.smooth_state()
+    s = fvm.Solver(c.mesh, c.task)
+    s.set_state(*st)
+    tau = s.calc_time_step()
+    o = P.OracleSolver(c.mesh, c.task)
+    o.set_state(*st)
+    assert o.calc_time_step() == tau
+    s.step(20)
+    assert o.step(20) == 0
+    e = pc.err_norm(s.get_state()[:4], o.get_state()[:4])
+    assert max(e) < TOL, e
+    pr, po = s.get_primitive(), o.get_primitive()
+    for k in pr:
+        assert relerr(pr[k], po[k]) < TOL, k
+    s.close(); o.close()
+
+
+def test_full_size_properties():
+    """BASELINE size (4 M cells): properties that do not need the oracle -- a uniform stream is a
+    fixed point of the scheme away from boundaries' influence, and mass is conserved to round-off in
+    a closed (all-wall) box."""
+    c = cases.strip(2000, 1000, jump="weak")          # 4 M cells, all walls
+    st = c.initial_state()
+    s = fvm.Solver(c.mesh, c.task)
+    s.set_state(*st)
+    s.calc_time_step()
+    m0 = float((st[0] * c.mesh.cell_S).sum())
+    e0 = float((st[3] * c.mesh.cell_S).sum())
+    s.step(10)
+    ro, ru, rv, re, ct, fl = s.get_state()
+    assert np.isfinite(ro).all() and (fl == 0).all()
+    assert abs(float((ro * c.mesh.cell_S).sum()) - m0) / m0 < 1e-13
+    assert abs(float((re * c.mesh.cell_S).sum()) - e0) / e0 < 1e-13
+    far = np.abs(c.mesh.cell_cx - 1000.0) > 200.0      # waves travel ~0.15 cell/step
+    assert np.array_equal(ro[far], st[0][far])         # untouched regions stay bit-identical
+    s.close()
+
+
+def test_newton_cap_surfaces_as_error():
+    c = cases.strip(20, 6, jump="sod")                 # 10:1 under 2nd-order Godunov: SURVEY F3
+    st = list(c.initial_state())
+    st[3] = st[3].copy()
+    st[3][: c.mesh.nc // 2] *= -1.0                    # negative energy -> negative pressure
+    s = fvm.Solver(c.mesh, c.task, max_newton=30)
+    s.set_state(*st)
+    s.calc_time_step()
+    with pytest.raises(fvm.CFDError) as e:
+        s.step(1)
+    assert e.value.code == -4
+    s.close()
+
+
+def test_empty_mesh_on_gpu():
+    from cfd2d_b200 import task as T
+    e = np.empty(0)
+    m = dict(cell_S=e, cell_cx=e, cell_cy=e, cell_mat=np.empty(0, np.int32), cell_edges=np.empty((0, 3), np.int32),
+             edge_c1=np.empty(0, np.int32), edge_c2=np.empty(0, np.int32), edge_nx=e, edge_ny=e, edge_l=e,
+             edge_gp=np.empty((0, 4)), edge_bc=np.empty(0, np.int32))
+    s = fvm.Solver(m, T.Task())
+    s.set_state(e, e, e, e)
+    s.calc_time_step()
+    s.step(2)
+    s.close()
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()
