@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the FVM_TVD hot path on B200, in the reference's metric.
+
+metric : cell-updates/sec per RK stage (FP64) = owned cells x 2 stages x steps / time
+step   : one whole RK2 time step of FVM_TVD::run (2 x [gradients, edge fluxes, residual gather,
+         update] + half-sum + limit flags + remediation), state resident in HBM
+e2e    : the same through the C-ABI with HOST buffers: every step uploads the conservative state
+         from pinned host memory (cfd2d_fvm_set_state), steps, and reads it back
+         (cfd2d_fvm_get_state) -- what the Method glue does at its save cadence
+workload (N=1): BASELINE.json configs[2], the configuration the roofline target is quoted on:
+         synthetic 2000x1000x2 = 4 M-cell triangulated channel (inlet / outlet / walls), smooth
+         initial data (the reference's 2nd-order path cannot run the literal shock IC),
+         2nd-order reconstruction + exact Godunov flux = the reference's live scheme.
+N>1    : weak scaling, 4 M cells per GPU (configs[4]); slab partition, owned/halo renumbering as
+         the reference's Decomp, NCCL send/recv halo exchange.
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                       [--flux godunov|lax] [--order 1|2] [--nx NX --ny NY]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ALGO_BYTES_STAGE = 320.0     # algorithmic bytes per cell per RK stage
+# split of the same inventory by kernel: what each kernel alone must touch
+ALGO_BYTES_KERNEL = {"grad": 32 + 64 + 8 + 1.5 * 24, "flux": 32 + 64 + 16 + 96, "update": 32 + 32 + 8 + 8}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_case(nx, ny):
+    from cfd2d_b200 import cases
+    c = cases.channel(nx, ny)
+    return c, c.smooth_state()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's own implementation (oracle/_ref when it loads, else the C port)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    nx, ny, nsteps, variant, flux, order, use_ref = args
+    import tempfile
+    from cfd2d_b200 import cases
+    c = cases.channel(nx, ny)
+    st = c.smooth_state()
+    if use_ref:
+        from oracle import refharness as R
+        d = tempfile.mkdtemp(prefix="cfd2d_ref_")
+        c.write(d)
+        s = R.RefSolver(d, variant=variant)
+        s.set_state(*st)
+        s.calc_time_step()
+        s.run(1)                       # warm caches / page in
+        dt = s.run(nsteps)
+    else:
+        from oracle import port as P
+        s = P.OracleSolver(c.mesh, c.task, flux, order)
+        s.set_state(*st)
+        s.calc_time_step()
+        s.step(1)
+        t0 = time.perf_counter()
+        s.step(nsteps)
+        dt = time.perf_counter() - t0
+    return c.mesh.nc * 2.0 * nsteps / dt, c.mesh.nc
+
+
+def cpu_reference(flux, order, nprocs=1, nx=500, ny=250, nsteps=6):
+    """Times the reference CPU solver on a bounded sample of the workload: a (nx x ny x 2)-cell twin
+    (same generator, BCs, initial data, scheme).  nprocs > 1 runs independent replicas concurrently
+    (FVM_TVD is serial: no OpenMP, no MPI calls) and sums their throughput."""
+    from oracle import refharness as R
+    variant = {(0, 2): "v0", (1, 1): "v1", (1, 2): "v2"}.get((flux, order))
+    use_ref = variant is not None and R.available(variant)
+    if use_ref:
+        try:
+            R.load(variant)
+        except OSError:
+            use_ref = False
+    args = (nx, ny, nsteps, variant, flux, order, use_ref)
+    if nprocs <= 1:
+        res = [_cpu_worker(args)]
+    else:
+        import multiprocessing as mp
+        with mp.get_context("spawn").Pool(nprocs) as pool:
+            res = pool.map(_cpu_worker, [args] * nprocs)
+    total = float(sum(r[0] for r in res))
+    return {"value": total, "unit": "cell-updates/s", "cores": int(nprocs),
+            "kind": "reference" if use_ref else "port",
+            "sample": f"{res[0][1]}-cell twin of the workload ({nx}x{ny}x2 channel, same BCs/IC/scheme), "
+                      f"{nsteps} RK2 steps after 1 warm-up step" + (f", {nprocs} independent replicas summed" if nprocs > 1 else ", 1 thread")}
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    flux = 0 if a.flux == "godunov" else 1
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(max(a.warmup, 0)):
+        pass                                          # each call below already does its own warm-up step
+    r = None
+    steps = max(1, min(a.steps, 3))
+    for _ in range(steps):
+        r = cpu_reference(flux, a.order, nprocs=cores)
+        vals.append(r["value"])
+        if time.perf_counter() - t0 > 150:
+            break
+    v = float(np.median(vals))
+    r["value"] = v
+    line = {"impl": "reference", "metric": "cell-updates/sec (FP64, RK stage)", "value": v, "unit": "cell-updates/s",
+            "n_gpus": a.gpus, "steps": len(vals), "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a), "cpu_baseline": r,
+            "e2e": {"value": v, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a):
+    return {"workload": f"BASELINE configs[2]: synthetic {a.nx}x{a.ny}x2 = {2 * a.nx * a.ny} -cell triangulated channel per GPU, "
+                        f"inlet/outlet/walls, smooth IC; RK2; order {a.order}; flux {a.flux}",
+            "cells_per_gpu": 2 * a.nx * a.ny, "flux": a.flux, "order": a.order,
+            "l2_policy": "inputs larger than L2 (working set ~1.9 GB at 4 M cells vs 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--flux", default="godunov", choices=["godunov", "lax"])
+    ap.add_argument("--order", type=int, default=2)
+    ap.add_argument("--nx", type=int, default=2000)
+    ap.add_argument("--ny", type=int, default=1000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra Lax-Friedrichs variant lines")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference_arm(a)
+        return
+    a.warmup = max(a.warmup, 3)
+
+    import torch
+    from cfd2d_b200 import fvm
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    flux = 0 if a.flux == "godunov" else 1
+    t_setup = time.perf_counter()
+    if world == 1:
+        c, st = workload_case(a.nx, a.ny)
+        s = fvm.Solver(c.mesh, c.task, flux, a.order, device=local)
+        nc_local, nc_total = c.mesh.nc, c.mesh.nc
+    else:
+        from cfd2d_b200 import decomp
+        s, st, nc_local, nc_total = decomp.make_rank_solver(a.nx, a.ny, rank, world, local, flux, a.order, dist)
+    stream = torch.cuda.current_stream()
+    s.set_stream(stream.cuda_stream)
+    s.set_state(*st)
+    s.calc_time_step()
+    setup_s = time.perf_counter() - t_setup
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing
+    s.step(a.warmup)
+    l0 = s.launch_count
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    s.step_async(a.steps)
+    e1.record(stream)
+    s.sync()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = s.launch_count - l0
+    clk = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    value = nc_total * 2.0 * a.steps / (ms * 1e-3)
+
+    # ---- per-kernel device time (CUDA events around every launch on the launching stream)
+    prof_steps = max(3, min(10, a.steps))
+    prof = s.profile(prof_steps)
+    stages = 2 * prof_steps
+    per_kernel = {}
+    for k, (tms, cnt) in prof.items():
+        if cnt:
+            per_kernel[k] = {"avg_ms": tms / cnt, "launches_per_step": cnt / prof_steps}
+    upd_ms = (prof["update1"][0] + prof["update2"][0]) / stages
+    grad_ms = prof["grad"][0] / stages if prof["grad"][1] else 0.0
+    flux_ms = prof["flux"][0] / stages
+    stage_ms = grad_ms + flux_ms + upd_ms
+    peak, peak_src = peaks()
+    ach_stage = ALGO_BYTES_STAGE * nc_local / (stage_ms * 1e-3) / 1e9
+    dom = max((("grad", grad_ms), ("flux", flux_ms), ("update", upd_ms)), key=lambda x: x[1])
+    ach_dom = ALGO_BYTES_KERNEL[dom[0]] * nc_local / (dom[1] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": ach_stage, "peak": peak, "unit": "GB/s", "frac": ach_stage / peak,
+                "traffic": None, "peak_source": peak_src,
+                "scope": "one RK stage = k_grad + k_flux + k_update (the 'residual+update' of the north star): "
+                         "320 algorithmic B/cell x owned cells / summed average launch durations",
+                "stage_ms": stage_ms,
+                "dominant_kernel": {"name": "k_" + dom[0], "avg_ms": dom[1], "share_of_stage": dom[1] / stage_ms,
+                                    "algorithmic_bytes_per_cell": ALGO_BYTES_KERNEL[dom[0]],
+                                    "achieved": ach_dom, "frac": ach_dom / peak},
+                "per_kernel": per_kernel}
+    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    if os.path.exists(tp):
+        try:
+            roofline["traffic"] = json.load(open(tp)).get("stage_dram_bytes_4m")
+        except Exception:
+            pass
+
+    # ---- e2e through the C-ABI with host buffers (pinned), H2D + step + D2H every step
+    pin = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in st]
+    out = [torch.empty(nc_local, dtype=torch.float64).pin_memory() for _ in range(4)]
+    ptr_in = [int(t.data_ptr()) for t in pin]
+    ptr_out = [int(t.data_ptr()) for t in out]
+    e2e_steps = max(3, min(10, a.steps))
+
+    def e2e_step():
+        s.set_state(*ptr_in)
+        s.step(1)
+        s.get_state(out=ptr_out, want_tau=False, want_flag=False)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e = {"value": nc_total * 2.0 * e2e_steps / e2e_s, "unit": "cell-updates/s",
+           "h2d_bytes_per_step": 32 * nc_local, "d2h_bytes_per_step": 32 * nc_local,
+           "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
+           "what": "cfd2d_fvm_set_state(pinned host) + cfd2d_fvm_step(1) + cfd2d_fvm_get_state(pinned host) per step"}
+
+    line = {"metric": "cell-updates/sec (FP64, RK stage)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "setup_s": setup_s}
+
+    # ---- the bandwidth-bound variants of the same path (reference's Lax-Friedrichs block), N=1 only
+    if world == 1 and not a.no_variants and flux == 0:
+        variants = {}
+        for name, (vf, vo) in {"lax_order2": (1, 2), "lax_order1": (1, 1)}.items():
+            s2 = fvm.Solver(c.mesh, c.task, vf, vo, device=local)
+            s2.set_stream(stream.cuda_stream)
+            s2.set_state(*st)
+            s2.calc_time_step()
+            s2.step(a.warmup)
+            torch.cuda.synchronize()
+            e0.record(stream); s2.step_async(a.steps); e1.record(stream); s2.sync()
+            vms = e0.elapsed_time(e1)
+            vv = nc_total * 2.0 * a.steps / (vms * 1e-3)
+            variants[name] = {"value": vv, "ms_per_step": vms / a.steps, "roofline_frac_320B": ALGO_BYTES_STAGE * vv / 1e9 / peak}
+            s2.close()
+        line["variants"] = variants
+
+    if rank == 0 and world == 1 and not a.no_cpu:
+        try:
+            line["cpu_baseline"] = cpu_reference(flux, a.order, nprocs=1)
+        except Exception as ex:  # the checker failing must not lose the GPU numbers
+            line["cpu_baseline"] = {"value": None, "error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    s.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
