@@ -230,7 +230,8 @@ def main():
     else:
         from cfd2d_b200 import decomp
         s, st, nc_local, nc_total = decomp.make_rank_solver(a.nx, a.ny, rank, world, local, flux, a.order, dist)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # a real (capturable) stream; torch events are recorded on it
+    torch.cuda.set_stream(stream)
     s.set_stream(stream.cuda_stream)
     s.set_state(*st)
     s.calc_time_step()

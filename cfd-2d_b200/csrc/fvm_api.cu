@@ -358,7 +358,7 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     TRY(dev_alloc(h, &h->Ua, (size_t)nc_ex));
     TRY(dev_alloc(h, &h->Ub, (size_t)nc_ex));
     TRY(dev_alloc(h, &h->W, (size_t)nc_ex));
-    TRY(dev_alloc(h, &h->G, 2 * (size_t)nc_ex));
+    TRY(dev_alloc(h, &h->G, 2 * (size_t)(nc_ex ? nc_ex : 1)));
     TRY(dev_alloc(h, &h->F, (size_t)ne));
     for (int i = 0; i < 6; i++) TRY(dev_alloc(h, &h->io[i], (size_t)nc));
     TRY(dev_alloc(h, &h->tau_bits, 1));

@@ -158,9 +158,9 @@ def test_medium_mesh_vs_oracle():
 
 
 def test_full_size_properties():
-    """BASELINE size (4 M cells): properties that do not need the oracle -- a uniform stream is a
-    fixed point of the scheme away from boundaries' influence, and mass is conserved to round-off in
-    a closed (all-wall) box."""
+    """BASELINE size (4 M cells): properties that do not need the oracle -- gas at rest stays at rest
+    (to round-off: the wall pressure terms p*n*l of a closed cell cancel only to ~1 ulp) away from the
+    initial jump, and mass and energy are conserved to round-off in a closed (all-wall) box."""
     c = cases.strip(2000, 1000, jump="weak")          # 4 M cells, all walls
     st = c.initial_state()
     s = fvm.Solver(c.mesh, c.task)
@@ -174,7 +174,11 @@ def test_full_size_properties():
     assert abs(float((ro * c.mesh.cell_S).sum()) - m0) / m0 < 1e-13
     assert abs(float((re * c.mesh.cell_S).sum()) - e0) / e0 < 1e-13
     far = np.abs(c.mesh.cell_cx - 1000.0) > 200.0      # waves travel ~0.15 cell/step
-    assert np.array_equal(ro[far], st[0][far])         # untouched regions stay bit-identical
+    assert np.abs(ro[far] / st[0][far] - 1.0).max() < 1e-13
+    assert np.abs(re[far] / st[3][far] - 1.0).max() < 1e-13
+    assert np.abs(ru[far]).max() < 1e-9 * np.abs(ro).max()
+    near = np.abs(c.mesh.cell_cx - 1000.0) < 3.0
+    assert np.abs(ru[near]).max() > 1.0                # while the jump itself has started to move
     s.close()
 
 
