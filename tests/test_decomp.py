@@ -1,0 +1,176 @@
+"""CPU: partition + owned/halo renumbering (cfd-2d_b200/decomp.py) against the reference's Decomp
+(run live from oracle/_ref when the reference tree is present, and against committed golden maps),
+plus a world_size-2 gloo test of the halo-exchange host logic."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from cfd2d_b200 import cases, decomp
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+HAVE_REF = os.path.exists("/root/reference/src/methods/decomp.cpp") and \
+    os.path.exists(os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "libcfd2d_ref_decomp.so"))
+
+
+def _case():
+    return cases.forward_step(40, 16, jitter=0.15)
+
+
+def _reference_maps(c, k):
+    import ctypes
+    import xml.etree.ElementTree as ET
+    d = tempfile.mkdtemp()
+    c.write(d)
+    tree = ET.parse(os.path.join(d, "task.xml"))
+    dec = ET.SubElement(tree.getroot(), "decomp")
+    ET.SubElement(dec, "processors", value=str(k))
+    tree.write(os.path.join(d, "task.xml"))
+    lib = ctypes.CDLL(os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "libcfd2d_ref_decomp.so"),
+                      mode=os.RTLD_LOCAL)
+    cwd = os.getcwd()
+    try:
+        assert lib.ref_decomp_run(d.encode(), b"task.xml") == 0
+    finally:
+        os.chdir(cwd)
+    txt = open(os.path.join(d, "parts.vtk")).read()
+    part = np.array(txt.split("LOOKUP_TABLE default\n")[1].split(), dtype=np.int32)
+    procs = [decomp.parse_proc_file(os.path.join(d, "mesh", "mesh.%04d.proc" % p)) for p in range(k)]
+    return part, procs
+
+
+def _check_against(c, k, part_ref, procs):
+    part = decomp.metis_part(c.mesh, k)
+    assert np.array_equal(part, part_ref)
+    rms = decomp.decompose(c.mesh, part, k)
+    for p, (rm, pf) in enumerate(zip(rms, procs)):
+        assert (rm.nc, rm.nc_ex) == (pf["cCount"], pf["cCountEx"])
+        assert (rm.g_edges.shape[0], rm.ne_ex) == (pf["eCount"], pf["eCountEx"])
+        assert np.array_equal(rm.recv_count, pf["recv_count"])
+        for q in range(k):
+            assert np.array_equal(rm.send_ind[q], pf["send_ind"][q]), (p, q)
+        # cells: the .proc file lists local node ids; compare through global node ids
+        # (node renumbering: owned-touching nodes ascending, then halo-only nodes)
+        node_in = np.zeros(c.mesh.nn, bool); node_in[c.mesh.cell_nodes[rm.g_cells[:rm.nc]].ravel()] = True
+        node_ex = np.zeros(c.mesh.nn, bool); node_ex[c.mesh.cell_nodes[rm.g_cells[rm.nc:]].ravel()] = True
+        g_nodes = np.concatenate([np.nonzero(node_in)[0], np.nonzero(node_ex & ~node_in)[0]])
+        assert (node_in.sum(), g_nodes.shape[0]) == (pf["nCount"], pf["nCountEx"])
+        assert np.array_equal(g_nodes[pf["cells"][:, 1:4]], c.mesh.cell_nodes[rm.g_cells])
+        ge_all = np.concatenate([rm.g_edges, rm.g_edges_ex])
+        assert np.array_equal(g_nodes[pf["edges"][:, 1]], c.mesh.edge_n1[ge_all])
+        assert np.array_equal(g_nodes[pf["edges"][:, 2]], c.mesh.edge_n2[ge_all])
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference tree / oracle/_ref not present")
+@pytest.mark.parametrize("k", [2, 4, 8])
+def test_maps_match_live_reference_decomp(k):
+    c = _case()
+    part, procs = _reference_maps(c, k)
+    _check_against(c, k, part, procs)
+    if k == 4 and os.environ.get("CFD2D_WRITE_GOLDEN"):
+        out = dict(part=part)
+        for p, pf in enumerate(procs):
+            out[f"recv_{p}"] = pf["recv_count"]
+            out[f"cells_{p}"] = pf["cells"]
+            out[f"counts_{p}"] = np.array([pf["cCount"], pf["cCountEx"], pf["eCount"], pf["eCountEx"]])
+            for q in range(k):
+                out[f"send_{p}_{q}"] = pf["send_ind"][q]
+        np.savez_compressed(os.path.join(G, "decomp_step40x16_k4.npz"), **out)
+
+
+@pytest.mark.skipif(not os.path.exists(decomp.METIS_LIB), reason="bundled METIS not built")
+def test_maps_match_golden_reference_decomp():
+    g = np.load(os.path.join(G, "decomp_step40x16_k4.npz"))
+    c = _case()
+    k = 4
+    part = decomp.metis_part(c.mesh, k)
+    assert np.array_equal(part, g["part"])
+    rms = decomp.decompose(c.mesh, part, k)
+    for p, rm in enumerate(rms):
+        assert np.array_equal([rm.nc, rm.nc_ex, rm.g_edges.shape[0], rm.ne_ex], g[f"counts_{p}"])
+        assert np.array_equal(rm.recv_count, g[f"recv_{p}"])
+        for q in range(k):
+            assert np.array_equal(rm.send_ind[q], g[f"send_{p}_{q}"])
+
+
+@pytest.mark.parametrize("k,how", [(2, "slab"), (3, "slab"), (4, "metis")])
+def test_decomposition_invariants(k, how):
+    c = cases.channel(24, 12, jitter=0.2, shuffle=True)
+    m = c.mesh
+    if how == "metis" and not os.path.exists(decomp.METIS_LIB):
+        pytest.skip("bundled METIS not built")
+    part = decomp.slab_part(m, k) if how == "slab" else decomp.metis_part(m, k)
+    rms = decomp.decompose(m, part, k)
+    assert sum(r.nc for r in rms) == m.nc
+    seen = np.concatenate([r.g_cells[:r.nc] for r in rms])
+    assert np.array_equal(np.sort(seen), np.arange(m.nc))
+    for r in rms:
+        loc = r.local
+        # every owned cell's three edges are local, the other side is owned or halo
+        assert loc["cell_edges"].shape == (r.nc, 3) and (loc["cell_edges"] >= 0).all()
+        assert (np.diff(loc["cell_edges"], axis=1) > 0).all()       # ascending: summation order preserved
+        assert loc["edge_c1"].max() < r.nc_ex and loc["edge_c2"].max() < r.nc_ex
+        # halo cells grouped by owner rank ascending (Grid::recvShift layout)
+        owners = part[r.g_cells[r.nc:]]
+        assert (np.diff(owners) >= 0).all()
+        assert np.array_equal(np.bincount(owners, minlength=k), r.recv_count)
+        # send lists mirror the receivers' halo slices
+        for q in range(k):
+            rq = rms[q]
+            sl = rq.g_cells[rq.nc:][part[rq.g_cells[rq.nc:]] == r.rank]
+            assert np.array_equal(r.g_cells[r.send_ind[q]], sl)
+        # geometry is the global edge's, orientation untouched
+        assert np.array_equal(loc["edge_nx"], m.edge_nx[r.g_edges])
+
+
+def _gloo_worker(rank, world, port, q):
+    """Each rank packs its send lists from a field = global cell id and exchanges with gloo the way
+    the CUDA halo module does with NCCL (pack -> send/recv -> contiguous halo slices)."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    c = cases.channel(24, 12, jitter=0.2, shuffle=True)
+    part = decomp.slab_part(c.mesh, world)
+    rm = decomp.decompose(c.mesh, part, world, only_rank=rank)[rank]
+    field = np.full(rm.nc_ex, -1.0)
+    field[:rm.nc] = rm.g_cells[:rm.nc]                       # owned cells carry their global id
+    ops, bufs = [], []
+    shift = np.concatenate([[0], np.cumsum(rm.recv_count)])
+    for p in range(world):
+        if p == rank:
+            continue
+        if len(rm.send_ind[p]):
+            t = torch.from_numpy(field[rm.send_ind[p]].copy())
+            ops.append(dist.P2POp(dist.isend, t, p)); bufs.append(t)
+        if rm.recv_count[p]:
+            t = torch.empty(int(rm.recv_count[p]), dtype=torch.float64)
+            ops.append(dist.P2POp(dist.irecv, t, p)); bufs.append((p, t))
+    for w in dist.batch_isend_irecv(ops):
+        w.wait()
+    for b in bufs:
+        if isinstance(b, tuple):
+            p, t = b
+            field[rm.nc + shift[p]: rm.nc + shift[p + 1]] = t.numpy()
+    ok = np.array_equal(field, rm.g_cells.astype(np.float64))  # every halo slot received ITS cell
+    tau = torch.tensor([1.0 + rank])
+    dist.all_reduce(tau, op=dist.ReduceOp.MIN)                 # the TAU reduction (calcTimeStep)
+    q.put((rank, bool(ok), float(tau.item())))
+    dist.destroy_process_group()
+
+
+def test_halo_exchange_logic_gloo_world2():
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=180) for _ in ps]
+    for p in ps:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res)
+    assert all(t == 1.0 for _, _, t in res)
