@@ -128,7 +128,7 @@ static void launch_grad(cfd2d_fvm* h) {
 static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale) {
     if (h->ne == 0) return;
     KTimer t(h, CFD2D_K_FLUX);
-    dim3 g(nblk(h->ne, 128)), b(128);
+    dim3 g(nblk(2 * (long long)h->ne, 128)), b(128);   // one thread per (edge, Gauss point)
     int fx = h->ctrl.flux, od = h->ctrl.order;
     if (fx == CFD2D_FLUX_GODUNOV && od == 2) k_flux<0, 2><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
     else if (fx == CFD2D_FLUX_GODUNOV) k_flux<0, 1><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);

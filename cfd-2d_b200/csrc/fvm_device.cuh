@@ -100,8 +100,6 @@ __device__ __forceinline__ int rim_orig_dev(const RimC& k, int max_newton,
     const double eps = 1.0e-5;
     double CB = sqrt(k.GAM * PB / RB);
     double CE = sqrt(k.GAM * PE / RE);
-    double EB = CB * CB / k.SGAM;
-    double EE = CE * CE / k.SGAM;
     double RCB = RB * CB;
     double RCE = RE * CE;
     double DU = UB - UE;
@@ -166,18 +164,20 @@ __device__ __forceinline__ int rim_orig_dev(const RimC& k, int max_newton,
     }
     // sampling at x/t = 0, global.cpp:353-400
     if (SEL <= 0.0) {
-        RI = RE; EI = EE; UI = UE; VI = VE;
+        RI = RE; EI = CE * CE / k.SGAM; UI = UE; VI = VE;            // EE, global.cpp:260
     } else if (SBL >= 0.0) {
-        RI = RB; EI = EB; UI = UB; VI = VB;
+        RI = RB; EI = CB * CB / k.SGAM; UI = UB; VI = VB;            // EB, global.cpp:259
     } else if ((SSL >= 0.0) && (SFL <= 0.0)) {
         if (US >= 0.0) { RI = RF; EI = EF; UI = UF; VI = VB; }
         else           { RI = RS; EI = ES; UI = US; VI = VE; }
     } else if (SFL > 0.0) {
+        double EB = CB * CB / k.SGAM;
         UI = (UB + k.DGGG * sqrt(EB)) / k.DG1;
         VI = VB;
         EI = (UI * UI) / k.SGAM;
         RI = RB * exp(log(EI / EB) * k.IAGAM);
     } else {
+        double EE = CE * CE / k.SGAM;
         UI = (UE - k.DGGG * sqrt(EE)) / k.DG1;
         VI = VE;
         EI = (UI * UI) / k.SGAM;

@@ -170,82 +170,82 @@ __global__ void __launch_bounds__(256) k_grad(KParams P, const double4* __restri
 // (FVM_TVD::reconstruct fvm_tvd.cpp:646-691, calcFlux :602-643, rim_orig global.cpp:232-405, the
 // Gauss-point loop of run() :341-352).  Writes F4[e] = (sum over GPs) * (l*0.5), the quantity the
 // reference scatters (:353-363).  FLUX: 0 Godunov, 1 Lax-Friedrichs.  ORDER: 2 linear, 1 constant.
+//
+// Work decomposition: ONE THREAD PER (edge, Gauss point); the two Gauss points of an edge sit in
+// adjacent lanes.  The exact Riemann solver is a long chain of dependent FP64 divisions/sqrt/exp/log
+// (latency bound at the ~12 warps/SM a 2-GP-per-thread version reaches, ncu profiles/r01_*), so
+// halving the per-thread state doubles the warps in flight, and lane pairs solve nearly identical
+// problems, which halves the number of distinct branch paths per warp.  The pair's fluxes are
+// combined with one shuffle: fr = (0.0 + fr1) + fr2 in the reference; IEEE addition commutes, so
+// both lanes form the same sum bit for bit; lane 0 stores (fr,fu), lane 1 stores (fv,fe).
 // ---------------------------------------------------------------------------------------------
+#ifndef CFD2D_FLUX_MINB
+#define CFD2D_FLUX_MINB 8
+#endif
 template <int FLUX, int ORDER>
-__global__ void __launch_bounds__(128) k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
-                                              const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2) {
-    int e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= P.ne) return;
+__global__ void __launch_bounds__(128, FLUX == 0 ? CFD2D_FLUX_MINB : 8)
+k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
+       const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = t >> 1;
+    const int gp = t & 1;
+    const bool live = e < P.ne;
+    if (!live) e = P.ne - 1;
     int2 cc = __ldg(P.e_c + e);
     double2 n = __ldg(P.e_n + e);
     double4 w1 = ld4(W, cc.x);
-    Prim c1 = {w1.x, w1.y, w1.z, w1.w};
-    Prim c2 = c1;
-    double E1 = 0.0, E2 = 0.0;
-    double4 d1 = make_double4(0, 0, 0, 0), d2 = d1, ga1 = d1, gb1 = d1, ga2 = d1, gb2 = d1;
-    if (ORDER == 2) {
-        d1 = ld4(P.e_d1, e);
-        ga1 = ld4(G, 2 * cc.x);
-        gb1 = ld4(G, 2 * cc.x + 1);
-    }
-    if (FLUX == 1) { double4 u = ld4(Ucur, cc.x); E1 = u.w / u.x; }
+    Prim L = {w1.x, w1.y, w1.z, w1.w};
+    Prim R;
+    double EL = 0.0, ER = 0.0;
+    if (FLUX == 1) { double4 u = ld4(Ucur, cc.x); EL = u.w / u.x; }
     const bool inner = cc.y >= 0;
-    MatC m; double T1 = 0.0; int kind = 0; const double* par = nullptr;
+    double T1 = 0.0;
+    MatC m;
+    if (!inner) { m = get_mat(P, cc.x); T1 = prim_T(L, m); }   // cell-centre T, before extrapolation
+    if (ORDER == 2) {
+        const double2* dp = reinterpret_cast<const double2*>(P.e_d1 + e) + gp;
+        double2 d = __ldg(dp);
+        double4 ga = ld4(G, 2 * cc.x), gb = ld4(G, 2 * cc.x + 1);
+        L.r += ga.x * d.x + ga.y * d.y;
+        L.p += ga.z * d.x + ga.w * d.y;
+        L.u += gb.x * d.x + gb.y * d.y;
+        L.v += gb.z * d.x + gb.w * d.y;
+    }
     if (inner) {
         double4 w2 = ld4(W, cc.y);
-        c2.r = w2.x; c2.p = w2.y; c2.u = w2.z; c2.v = w2.w;
+        R.r = w2.x; R.p = w2.y; R.u = w2.z; R.v = w2.w;
+        if (FLUX == 1) { double4 u = ld4(Ucur, cc.y); ER = u.w / u.x; }
         if (ORDER == 2) {
-            d2 = ld4(P.e_d2, e);
-            ga2 = ld4(G, 2 * cc.y);
-            gb2 = ld4(G, 2 * cc.y + 1);
+            const double2* dp = reinterpret_cast<const double2*>(P.e_d2 + e) + gp;
+            double2 d = __ldg(dp);
+            double4 ga = ld4(G, 2 * cc.y), gb = ld4(G, 2 * cc.y + 1);
+            R.r += ga.x * d.x + ga.y * d.y;
+            R.p += ga.z * d.x + ga.w * d.y;
+            R.u += gb.x * d.x + gb.y * d.y;
+            R.v += gb.z * d.x + gb.w * d.y;
         }
-        if (FLUX == 1) { double4 u = ld4(Ucur, cc.y); E2 = u.w / u.x; }
     } else {
-        m = get_mat(P, cc.x);
-        T1 = prim_T(c1, m);
         int ib = __ldg(P.e_bc + e);
-        kind = P.bc_kind[ib];
-        par = P.bc_par + 4 * ib;
+        R = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
     }
-    double fr = 0.0, fu = 0.0, fv = 0.0, fe = 0.0;
-    int bad = 0;
-#pragma unroll
-    for (int gp = 0; gp < 2; gp++) {
-        Prim L = c1, R = c2;
-        double ER = E2;
-        if (ORDER == 2) {
-            double dx = gp ? d1.z : d1.x, dy = gp ? d1.w : d1.y;
-            L.r += ga1.x * dx + ga1.y * dy;
-            L.p += ga1.z * dx + ga1.w * dy;
-            L.u += gb1.x * dx + gb1.y * dy;
-            L.v += gb1.z * dx + gb1.w * dy;
-        }
-        if (inner) {
-            if (ORDER == 2) {
-                double dx = gp ? d2.z : d2.x, dy = gp ? d2.w : d2.y;
-                R.r += ga2.x * dx + ga2.y * dy;
-                R.p += ga2.z * dx + ga2.w * dy;
-                R.u += gb2.x * dx + gb2.y * dy;
-                R.v += gb2.z * dx + gb2.w * dy;
-            }
-        } else {
-            R = ghost_state(L, T1, kind, par, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
-        }
-        double f0, f1, f2, f3;
-        if (FLUX == 0) {
-            int it = flux_godunov_dev(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
-            bad |= (it < 0);
-        } else {
-            flux_lax_dev(P.rim.GAM, L, E1, R, ER, n.x, n.y, f0, f1, f2, f3);
-        }
-        fr += f0; fu += f1; fv += f2; fe += f3;
+    double f0, f1, f2, f3;
+    if (FLUX == 0) {
+        int it = flux_godunov_dev(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
+        if (it < 0 && live) atomicAdd(P.err, 1);
+    } else {
+        flux_lax_dev(P.rim.GAM, L, EL, R, ER, n.x, n.y, f0, f1, f2, f3);
     }
-    if (bad) atomicAdd(P.err, 1);
+    // this lane keeps two of the four sums: lane 0 (fr,fu), lane 1 (fv,fe)
+    double a = gp ? f2 : f0, b = gp ? f3 : f1;       // mine
+    double oa = gp ? f0 : f2, ob = gp ? f1 : f3;     // the partner's pair
+    double pa = __shfl_xor_sync(0xffffffffu, oa, 1), pb = __shfl_xor_sync(0xffffffffu, ob, 1);
+    double sa = gp ? (pa + a) : (a + pa);            // (0.0 + f_gp1) + f_gp2
+    double sb = gp ? (pb + b) : (b + pb);
     if (scale_by_l2) {
         double l2 = __ldg(P.e_l2 + e);
-        fr = fr * l2; fu = fu * l2; fv = fv * l2; fe = fe * l2;
+        sa = sa * l2; sb = sb * l2;
     }
-    st4(F, e, make_double4(fr, fu, fv, fe));
+    if (live) reinterpret_cast<double2*>(F + e)[gp] = make_double2(sa, sb);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ from . import mesh as _mesh
 from . import task as _task
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libcfd2d_b200.so")
+LIB_PATH = os.environ.get("CFD2D_LIB") or os.path.join(HERE, "csrc", "libcfd2d_b200.so")   # env: kernel-variant sweeps only
 
 FLUX_GODUNOV, FLUX_LAX = 0, 1
 K_NAMES = ["grad", "flux", "update1", "update2", "remediate", "timestep", "halo"]

@@ -181,6 +181,11 @@ int cfd2d_fvm_set_stream(cfd2d_fvm* h, void* cuda_stream);
 /* Enable/disable CUDA-graph replay of the step (default on).                                      */
 int cfd2d_fvm_use_graph(cfd2d_fvm* h, int on);
 
+/* Multi-rank bootstrap: a 128-byte ncclUniqueId created on one rank (ncclGetUniqueId); the caller
+ * ships it to the other ranks (MPI_Bcast in the reference host, torch.distributed here) and every
+ * rank passes it in cfd2d_halo.nccl_unique_id.                                                    */
+int cfd2d_nccl_get_unique_id(void* out128);
+
 const char* cfd2d_fvm_last_error(const cfd2d_fvm* h);   /* h == NULL -> last create() error         */
 const char* cfd2d_version(void);
 

@@ -1,0 +1,61 @@
+"""torchrun worker: multi-GPU run == single-GPU run, bit for bit.
+Launched by tests/test_gpu_multi.py as
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tests/multigpu_worker.py
+Each rank owns one GPU, one METIS/slab subdomain and exchanges halo cells over NCCL send/recv."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from cfd2d_b200 import cases, decomp, fvm
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for partition, flux, order, steady in (("metis", 0, 2, 0), ("slab", 1, 2, 0), ("metis", 1, 1, 0), ("slab", 0, 2, 1)):
+        c = cases.channel(96, 48, jitter=0.2, shuffle=True)
+        c.task.steady = steady
+        st = c.smooth_state()
+        if partition == "metis" and not os.path.exists(decomp.METIS_LIB):
+            partition = "slab"
+        s, st_loc, nc_loc, nc_tot = decomp.make_rank_solver(0, 0, rank, world, local, flux, order, dist,
+                                                            partition=partition, case=c, state=st)
+        s.set_state(*st_loc)
+        tau = s.calc_time_step()
+        s.step(12)
+        got = s.get_state()
+        rm = s.rank_mesh
+        # assemble the global state on every rank
+        glob = [torch.zeros(nc_tot, dtype=torch.float64, device="cuda") for _ in range(4)]
+        idx = torch.from_numpy(rm.g_cells[:rm.nc].astype(np.int64)).cuda()
+        for k in range(4):
+            glob[k][idx] = torch.from_numpy(got[k]).cuda()
+            dist.all_reduce(glob[k])
+        s.close()
+        if rank == 0:
+            s1 = fvm.Solver(c.mesh, c.task, flux, order, device=local)
+            s1.set_state(*st)
+            tau1 = s1.calc_time_step()
+            s1.step(12)
+            ref = s1.get_state()
+            s1.close()
+            same = all(np.array_equal(glob[k].cpu().numpy(), ref[k]) for k in range(4)) and tau == tau1
+            print(f"[multi-gpu x{world}] partition={partition} flux={flux} order={order} steady={steady}: "
+                  f"bitwise equal to 1 GPU = {same}, tau={tau}", flush=True)
+            ok = ok and same
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

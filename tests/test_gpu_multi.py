@@ -1,0 +1,30 @@
+"""GPU (-m gpu): multi-GPU path (needs >= 2 GPUs, otherwise skipped): METIS / slab partition, owned/halo
+renumbering, NCCL send/recv halo exchange -- the assembled state must equal the single-GPU state
+bit for bit (same kernels, same per-cell summation order, global edge orientation on every rank)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.parametrize("n", [2, 4])
+def test_multi_gpu_equals_single_gpu_bitwise(n):
+    if _ngpu() < n:
+        pytest.skip(f"needs {n} GPUs")
+    port = 29600 + n
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "multigpu_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-4000:])
+    sys.stderr.write(r.stderr[-4000:])
+    assert r.returncode == 0
+    assert r.stdout.count("bitwise equal to 1 GPU = True") == 4
