@@ -40,6 +40,7 @@ struct cfd2d_fvm {
     int64_t launches = 0;
     // halo
     HaloNccl* halo = nullptr;
+    std::vector<int> edge_pos;   // caller's edge id -> position in the device edge arrays (create())
     std::string error;
 };
 
@@ -268,6 +269,48 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return CFD2D_ECUDA; }
         cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
     }
+    // ---- internal edge order.  The flux kernel may visit edges in any order (each edge is independent,
+    // F is addressed through the per-cell slot table, whose SLOT order -- the summation order -- is
+    // untouched).  Edges are grouped by the direction of their normal (16 bins over [0, pi)), inner
+    // edges first, boundary edges last, ascending id within a group.  Why: whether the two waves of
+    // the Riemann problem are shocks or rarefactions is decided by the sign of (uL-uR).n, i.e. by the
+    // local velocity gradient contracted twice with n -- spatially smooth for a fixed direction but
+    // alternating between the three edge directions of a triangle.  Grouping by direction makes the
+    // exp/log (rarefaction) vs sqrt/div (shock) branches of rim_orig warp-coherent; it also makes
+    // the c1/c2 gathers of consecutive lanes monotone in memory.
+    // The grouping is done inside tiles of EDGE_TILE consecutive edges, so that the cells a tile
+    // touches (a few MB of W/G records) stay in L2 while its direction groups are swept one after
+    // the other -- without tiling every group pass would stream all cell records from HBM again.
+    const int NBIN = 16;
+    int EDGE_TILE = 65536;
+    if (const char* ev = getenv("CFD2D_EDGE_TILE")) EDGE_TILE = atoi(ev);   // 0 = keep the caller's order
+    std::vector<int> order(ne), epos(ne);
+    {
+        const double PI_ = 3.14159265358979323846;
+        std::vector<int> key(ne);
+        for (int e = 0; e < ne; e++) {
+            int b;
+            if (m->edge_c2[e] < 0) b = NBIN;                      // boundary edges: own group, last
+            else {
+                double a = atan2(m->edge_ny[e], m->edge_nx[e]);   // (-pi, pi]
+                if (a < 0) a += PI_;                              // fold n and -n together
+                b = (int)floor((a + PI_ / (2 * NBIN)) / (PI_ / NBIN));
+                if (b >= NBIN || b < 0) b = 0;
+            }
+            key[e] = b;
+        }
+        if (EDGE_TILE <= 0) { for (int e = 0; e < ne; e++) { order[e] = e; epos[e] = e; } }
+        else {
+            for (int t0 = 0; t0 < ne; t0 += EDGE_TILE) {
+                int t1 = t0 + EDGE_TILE < ne ? t0 + EDGE_TILE : ne;
+                int cnt[NBIN + 2] = {0};
+                for (int e = t0; e < t1; e++) cnt[key[e] + 1]++;
+                for (int b = 0; b <= NBIN; b++) cnt[b + 1] += cnt[b];
+                for (int e = t0; e < t1; e++) { int q = t0 + cnt[key[e]]++; order[q] = e; epos[e] = q; }
+            }
+        }
+    }
+    h->edge_pos = epos;
     // ---- per (cell, slot) gather tables
     std::vector<int> s_nb(3 * (size_t)nc), s_es(3 * (size_t)nc);
     std::vector<double> s_nx(3 * (size_t)nc), s_ny(3 * (size_t)nc), s_l(3 * (size_t)nc);
@@ -279,11 +322,11 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
             if (m->edge_c1[e] == cc) {
                 s_nb[o] = m->edge_c2[e] >= 0 ? m->edge_c2[e] : -1 - m->edge_bc[e];
                 s_nx[o] = m->edge_nx[e]; s_ny[o] = m->edge_ny[e];
-                s_es[o] = e * 2;
+                s_es[o] = epos[e] * 2;
             } else if (m->edge_c2[e] == cc) {
                 s_nb[o] = m->edge_c1[e];
                 s_nx[o] = -m->edge_nx[e]; s_ny[o] = -m->edge_ny[e];
-                s_es[o] = e * 2 + 1;
+                s_es[o] = epos[e] * 2 + 1;
             } else {
                 g_create_error = "cell_edges names an edge that does not touch the cell";
                 cfd2d_fvm_destroy(h);
@@ -297,16 +340,19 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     std::vector<double2> e_n(ne);
     std::vector<double> e_l2(ne);
     std::vector<double4> e_d1(ne), e_d2(ne);
-    for (int e = 0; e < ne; e++) {
+    std::vector<int> ebc(ne);
+    for (int q = 0; q < ne; q++) {
+        const int e = order[q];                                       // caller's edge id
         int c1 = m->edge_c1[e], c2 = m->edge_c2[e];
-        e_c[e] = make_int2(c1, c2);
-        e_n[e] = make_double2(m->edge_nx[e], m->edge_ny[e]);
-        e_l2[e] = m->edge_l[e] * 0.5;                                 // fvm_tvd.cpp:335
+        e_c[q] = make_int2(c1, c2);
+        e_n[q] = make_double2(m->edge_nx[e], m->edge_ny[e]);
+        e_l2[q] = m->edge_l[e] * 0.5;                                 // fvm_tvd.cpp:335
+        ebc[q] = m->edge_bc[e];
         const double* g = m->edge_gp + 4 * (size_t)e;
         // DL = PE - P(cell) (fvm_tvd.cpp:661-664): the same subtraction, done once
-        e_d1[e] = make_double4(g[0] - m->cell_cx[c1], g[1] - m->cell_cy[c1], g[2] - m->cell_cx[c1], g[3] - m->cell_cy[c1]);
-        if (c2 >= 0) e_d2[e] = make_double4(g[0] - m->cell_cx[c2], g[1] - m->cell_cy[c2], g[2] - m->cell_cx[c2], g[3] - m->cell_cy[c2]);
-        else e_d2[e] = make_double4(0, 0, 0, 0);
+        e_d1[q] = make_double4(g[0] - m->cell_cx[c1], g[1] - m->cell_cy[c1], g[2] - m->cell_cx[c1], g[3] - m->cell_cy[c1]);
+        if (c2 >= 0) e_d2[q] = make_double4(g[0] - m->cell_cx[c2], g[1] - m->cell_cy[c2], g[2] - m->cell_cx[c2], g[3] - m->cell_cy[c2]);
+        else e_d2[q] = make_double4(0, 0, 0, 0);
     }
     std::vector<MatC> mats(p->nmat);
     for (int i = 0; i < p->nmat; i++) {
@@ -322,7 +368,6 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     std::vector<int> bkind(p->bc_kind, p->bc_kind + p->nbc);
     std::vector<double> bpar(p->bc_par, p->bc_par + 4 * (size_t)p->nbc);
     std::vector<double> cS(m->cell_S, m->cell_S + nc_ex);
-    std::vector<int> ebc(m->edge_bc, m->edge_bc + ne);
 
     KParams& P = h->P;
     P.nc = nc; P.nc_ex = nc_ex; P.ne = ne; P.nmat = p->nmat;
@@ -569,9 +614,11 @@ int cfd2d_fvm_edge_fluxes(cfd2d_fvm* h, double* flux4) {
     int rc;
     if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h))) return rc; }
     launch_flux(h, h->Ua, 0);
-    CUDA_TRY(h, cudaMemcpyAsync(flux4, h->F, (size_t)h->ne * 32, cudaMemcpyDeviceToHost, h->stream));
+    std::vector<double> tmp(4 * (size_t)h->ne);
+    CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), h->F, (size_t)h->ne * 32, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
+    for (int e = 0; e < h->ne; e++) memcpy(flux4 + 4 * (size_t)e, tmp.data() + 4 * (size_t)h->edge_pos[e], 32);
     return check_device_errors(h);
 }
 

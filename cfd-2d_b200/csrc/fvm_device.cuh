@@ -89,35 +89,82 @@ __device__ __forceinline__ void rim_side(const RimC& k, double P, double PS, dou
     }
 }
 
+// One side of the Riemann problem in the edge frame: s = -1 for the left state "B", +1 for the right
+// state "E".  The reference writes the two sides out separately with opposite signs
+// (global.cpp:318-349); x + (-1)*y == x - y exactly, so one signed routine reproduces both.
+struct RimSide { double R, P, U, V, C, RC, s; };
+struct RimWave { bool rar; double ZD; double Ustar; double head, tail; };
+
+// wave speeds of one side for the converged P (global.cpp:318-349)
+__device__ __forceinline__ void rim_waves(const RimC& k, double P, const RimSide& S, RimWave& w) {
+    w.rar = S.P > P;
+    if (w.rar) {                                   // lbl6 / lbl8: rarefaction
+        double ZF = S.C * exp(log(P / S.P) * k.OGAM);
+        w.Ustar = S.U - S.s * (k.DGAM * (S.C - ZF));
+        w.head = S.U + S.s * S.C;
+        w.tail = w.Ustar + S.s * ZF;
+        w.ZD = ZF;
+    } else {                                       // shock moving with speed D
+        double D = S.U + S.s * sqrt((k.TGAM * P + k.HGAM * S.P) / S.R);
+        w.Ustar = 0.0;
+        w.head = D;
+        w.tail = D;
+        w.ZD = D;
+    }
+}
+
+// density and velocity behind a shock (global.cpp:321-324 / :338-341)
+__device__ __forceinline__ void rim_shock_star(double P, const RimSide& S, double D, double& Rst, double& Ust) {
+    double UD = S.U - D;
+    double RUD = S.R * UD;
+    Rst = RUD * RUD / (S.P - P + RUD * UD);
+    Ust = D + RUD / Rst;
+}
+
 // rim_orig (global.cpp:232-405) with WB = WE = 0.  Quantities the reference computes but never
-// reads on the taken path (e.g. ZFB on a shock side, global.cpp:315) are skipped; every value that
-// is used is formed by the reference's own expression.  Returns the Newton iteration count, or -1
-// if `max_newton` was reached (the reference has no cap and would hang).
+// reads on the taken path (e.g. ZFB on a shock side, global.cpp:315; the star state of the side the
+// sampling does not select) are skipped; every value that is used is formed by the reference's own
+// expression.  Branch coherence: both the Newton function and the wave speeds are evaluated for the
+// HIGHER-pressure side first -- whenever the star pressure lies between PB and PE (all smooth-flow
+// edges) every lane of a warp then takes the rarefaction branch in the first call and the shock
+// branch in the second, whatever the edge orientation; results are mapped back to (B, E) before any
+// order-sensitive arithmetic.  Returns the Newton iteration count, or -1 if `max_newton` was
+// reached (the reference has no cap and would hang).
 __device__ __forceinline__ int rim_orig_dev(const RimC& k, int max_newton,
                                             double RB, double PB, double UB, double VB,
                                             double RE, double PE, double UE, double VE,
                                             double& RI, double& EI, double& PI, double& UI, double& VI) {
     const double eps = 1.0e-5;
-    double CB = sqrt(k.GAM * PB / RB);
-    double CE = sqrt(k.GAM * PE / RE);
-    double RCB = RB * CB;
-    double RCE = RE * CE;
+    RimSide B, E;
+    B.R = RB; B.P = PB; B.U = UB; B.V = VB; B.s = -1.0;
+    E.R = RE; E.P = PE; E.U = UE; E.V = VE; E.s = 1.0;
+    B.C = sqrt(k.GAM * PB / RB);
+    E.C = sqrt(k.GAM * PE / RE);
+    B.RC = RB * B.C;
+    E.RC = RE * E.C;
     double DU = UB - UE;
-    double US = 0.0, UF = 0.0, RF = 0.0, RS = 0.0, EF = 0.0, ES = 0.0;
-    double SBL, SFL, SSL, SEL;
+    double P = 0.0;
+    RimWave wB, wE;
+    bool vacuum = false;
     int it = 0;
-    if (DU < -2.0 * (CB + CE) / k.AGAM) {          // vacuum, global.cpp:265-276
-        SBL = UB - CB;
-        SFL = UB + 2.0 * CB / k.AGAM;
-        SSL = UE - 2.0 * CE / k.AGAM;
-        SEL = UE + CE;
+    if (DU < -2.0 * (B.C + E.C) / k.AGAM) {        // vacuum, global.cpp:265-276 (RF=RS=EF=ES=UF=US=0)
+        vacuum = true;
+        wB.rar = wE.rar = false; wB.ZD = wE.ZD = 0.0; wB.Ustar = wE.Ustar = 0.0;
+        wB.head = UB - B.C;                        // SBL
+        wB.tail = UB + 2.0 * B.C / k.AGAM;         // SFL
+        wE.tail = UE - 2.0 * E.C / k.AGAM;         // SSL
+        wE.head = UE + E.C;                        // SEL
     } else {
-        double P = (PB * RCE + PE * RCB + DU * RCB * RCE) / (RCB + RCE);   // global.cpp:277
+        const bool sw = PE > PB;                   // hi = E when the right pressure is larger
+        const RimSide hi = sw ? E : B, lo = sw ? B : E;
+        P = (PB * E.RC + PE * B.RC + DU * B.RC * E.RC) / (B.RC + E.RC);   // global.cpp:277
         for (;;) {
             if (P < eps) P = eps;
-            double F1, FS1, F2, FS2;
-            rim_side(k, P, PB, CB, RCB, F1, FS1);
-            rim_side(k, P, PE, CE, RCE, F2, FS2);
+            double Fh, FSh, Fl, FSl;
+            rim_side(k, P, hi.P, hi.C, hi.RC, Fh, FSh);
+            rim_side(k, P, lo.P, lo.C, lo.RC, Fl, FSl);
+            double F1 = sw ? Fl : Fh, F2 = sw ? Fh : Fl;          // back to (B, E) order
+            double FS1 = sw ? FSl : FSh, FS2 = sw ? FSh : FSl;
             double res = DU - F1 - F2;
             double DP = res / (FS1 + FS2);
             P = P + DP;
@@ -125,59 +172,51 @@ __device__ __forceinline__ int rim_orig_dev(const RimC& k, int max_newton,
             if (!(fabs(res) > eps)) break;
             if (it >= max_newton) { it = -1; break; }
         }
-        double PPB = P / PB;
-        double PPE = P / PE;
-        if (PB > P) {                              // lbl6: left rarefaction
-            double ZFB = CB * exp(log(PPB) * k.OGAM);
-            EF = ZFB * ZFB / k.SGAM;
-            UF = UB + k.DGAM * (CB - ZFB);
-            RF = P / (k.AGAM * EF);
-            SBL = UB - CB;
-            SFL = UF - ZFB;
-        } else {                                   // left shock
-            double D = UB - sqrt((k.TGAM * P + k.HGAM * PB) / RB);
-            double UBD = UB - D;
-            double RUBD = RB * UBD;
-            RF = RUBD * RUBD / (PB - P + RUBD * UBD);
-            UF = D + RUBD / RF;
-            EF = P / (k.AGAM * RF);
-            SBL = D;
-            SFL = D;
-        }
-        if (PE > P) {                              // lbl8: right rarefaction
-            double ZFE = CE * exp(log(PPE) * k.OGAM);
-            ES = ZFE * ZFE / k.SGAM;
-            US = UE - k.DGAM * (CE - ZFE);
-            RS = P / (k.AGAM * ES);
-            SSL = US + ZFE;
-            SEL = UE + CE;
-        } else {                                   // right shock
-            double D = UE + sqrt((k.TGAM * P + k.HGAM * PE) / RE);
-            double UED = UE - D;
-            double RUED = RE * UED;
-            RS = RUED * RUED / (PE - P + RUED * UED);
-            US = D + RUED / RS;
-            ES = P / (k.AGAM * RS);
-            SEL = D;
-            SSL = D;
-        }
+        RimWave wh, wl;
+        rim_waves(k, P, hi, wh);
+        rim_waves(k, P, lo, wl);
+        wB = sw ? wl : wh;
+        wE = sw ? wh : wl;
     }
+    const double SBL = wB.head, SFL = wB.tail, SSL = wE.tail, SEL = wE.head;
     // sampling at x/t = 0, global.cpp:353-400
     if (SEL <= 0.0) {
-        RI = RE; EI = CE * CE / k.SGAM; UI = UE; VI = VE;            // EE, global.cpp:260
+        RI = RE; EI = E.C * E.C / k.SGAM; UI = UE; VI = VE;          // EE, global.cpp:260
     } else if (SBL >= 0.0) {
-        RI = RB; EI = CB * CB / k.SGAM; UI = UB; VI = VB;            // EB, global.cpp:259
+        RI = RB; EI = B.C * B.C / k.SGAM; UI = UB; VI = VB;          // EB, global.cpp:259
     } else if ((SSL >= 0.0) && (SFL <= 0.0)) {
-        if (US >= 0.0) { RI = RF; EI = EF; UI = UF; VI = VB; }
-        else           { RI = RS; EI = ES; UI = US; VI = VE; }
+        double RS = 0.0, US = wE.Ustar;
+        if (!vacuum && !wE.rar) rim_shock_star(P, E, wE.ZD, RS, US);   // US decides the side
+        if (US >= 0.0) {                           // left star state
+            double RF = 0.0, EF = 0.0, UF = wB.Ustar;
+            if (!vacuum) {
+                if (wB.rar) {
+                    EF = wB.ZD * wB.ZD / k.SGAM;
+                    RF = P / (k.AGAM * EF);
+                } else {
+                    rim_shock_star(P, B, wB.ZD, RF, UF);
+                    EF = P / (k.AGAM * RF);
+                }
+            }
+            RI = RF; EI = EF; UI = UF; VI = VB;
+        } else {                                   // right star state
+            double ES;
+            if (wE.rar) {
+                ES = wE.ZD * wE.ZD / k.SGAM;
+                RS = P / (k.AGAM * ES);
+            } else {
+                ES = P / (k.AGAM * RS);
+            }
+            RI = RS; EI = ES; UI = US; VI = VE;
+        }
     } else if (SFL > 0.0) {
-        double EB = CB * CB / k.SGAM;
+        double EB = B.C * B.C / k.SGAM;
         UI = (UB + k.DGGG * sqrt(EB)) / k.DG1;
         VI = VB;
         EI = (UI * UI) / k.SGAM;
         RI = RB * exp(log(EI / EB) * k.IAGAM);
     } else {
-        double EE = CE * CE / k.SGAM;
+        double EE = E.C * E.C / k.SGAM;
         UI = (UE - k.DGGG * sqrt(EE)) / k.DG1;
         VI = VE;
         EI = (UI * UI) / k.SGAM;
