@@ -3,6 +3,7 @@
 // number the caller gets back was produced by the kernels in fvm_kernels.cuh.
 #include "../../include/cfd2d_fvm.h"
 #include "fvm_kernels.cuh"
+#include "fvm_fused.cuh"
 #include "halo_nccl.h"
 
 #include <cmath>
@@ -24,7 +25,20 @@ struct cfd2d_fvm {
     bool own_stream = true;
     // device buffers
     std::vector<void*> allocs;
-    double4 *Ua = nullptr, *Ub = nullptr, *W = nullptr, *G = nullptr, *F = nullptr;
+    double4 *Ua = nullptr, *Ub = nullptr, *W = nullptr, *Wb = nullptr, *G = nullptr, *F = nullptr;
+    uint32_t* io_u32 = nullptr;   // flag staging (caller order)
+    // tile-fused stage kernel (fvm_fused.cuh)
+    bool fused = true;
+    FParams Q{};
+    int ntiles = 0, n_interior = 0, n_boundary = 0, stage_nt = 256;
+    size_t stage_smem = 0;
+    int *d_interior = nullptr, *d_boundary = nullptr;
+    int* d_send_dev = nullptr;    // send cells (device ids), all peers
+    int n_send = 0;
+    cudaStream_t comm = nullptr;  // halo exchange stream (multi-rank handles)
+    cudaEvent_t ev_G = nullptr, ev_stage = nullptr, ev_U = nullptr;
+    std::vector<int> perm, orig;  // caller <-> device cell numbering
+    std::string plan_summary;
     double* io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // SoA staging for set/get
     unsigned long long* tau_bits = nullptr;
     int* err = nullptr;
@@ -99,12 +113,14 @@ static RimC make_rim(double GAM) {
 
 // ---- kernel launch helpers with optional per-kernel event timing ---------------------------
 struct KTimer {
-    cfd2d_fvm* h; int id;
-    KTimer(cfd2d_fvm* h_, int id_) : h(h_), id(id_) { if (h->profiling) cudaEventRecord(h->ev0, h->stream); }
+    cfd2d_fvm* h; int id; cudaStream_t st;
+    KTimer(cfd2d_fvm* h_, int id_, cudaStream_t st_ = nullptr) : h(h_), id(id_), st(st_ ? st_ : h_->stream) {
+        if (h->profiling) cudaEventRecord(h->ev0, st);
+    }
     ~KTimer() {
         h->launches++;
         if (h->profiling) {
-            cudaEventRecord(h->ev1, h->stream);
+            cudaEventRecord(h->ev1, st);
             cudaEventSynchronize(h->ev1);
             float ms = 0.f;
             cudaEventElapsedTime(&ms, h->ev0, h->ev1);
@@ -114,16 +130,16 @@ struct KTimer {
     }
 };
 
-static void launch_prim(cfd2d_fvm* h, const double4* U, int c0, int c1) {
+static void launch_prim(cfd2d_fvm* h, const double4* U, double4* W, int c0, int c1, cudaStream_t st) {
     if (c1 <= c0) return;
     h->launches++;
-    k_prim<<<nblk(c1 - c0, 256), 256, 0, h->stream>>>(h->P, U, h->W, c0, c1);
+    k_prim<<<nblk(c1 - c0, 256), 256, 0, st>>>(h->P, U, W, c0, c1);
 }
 
 static void launch_grad(cfd2d_fvm* h) {
     if (h->nc == 0) return;
     KTimer t(h, CFD2D_K_GRAD);
-    k_grad<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->W, h->G);
+    k_grad<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->W, h->G, nullptr, h->nc);
 }
 
 static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale) {
@@ -155,42 +171,129 @@ static void launch_tau_steady(cfd2d_fvm* h) {
     k_tau_steady<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->W);
 }
 
-// halo exchange of U4 (rec4 = 1) into `U`'s halo slice followed by the halo prim conversion, or of
-// G8 (rec4 = 2).  Method::exchange semantics (method.h:13-41): recv lands contiguously at recvShift.
-static int exchange_U(cfd2d_fvm* h, double4* U) {
+// ---- the tile-fused stage kernel: template dispatch over (flux, order, stage, block size) ------
+typedef void (*stage_fn)(KParams, FParams, const double4*, const double4*, double4*, double4*, const double4*);
+
+template <int NT, int MINB>
+static stage_fn stage_kernel_nt(int flux, int order, int stage) {
+    if (flux == CFD2D_FLUX_GODUNOV) {
+        if (order == 2) return stage == 1 ? (stage_fn)k_stage<0, 2, 1, NT, MINB> : (stage_fn)k_stage<0, 2, 2, NT, MINB>;
+        return stage == 1 ? (stage_fn)k_stage<0, 1, 1, NT, MINB> : (stage_fn)k_stage<0, 1, 2, NT, MINB>;
+    }
+    if (order == 2) return stage == 1 ? (stage_fn)k_stage<1, 2, 1, NT, MINB> : (stage_fn)k_stage<1, 2, 2, NT, MINB>;
+    return stage == 1 ? (stage_fn)k_stage<1, 1, 1, NT, MINB> : (stage_fn)k_stage<1, 1, 2, NT, MINB>;
+}
+
+static stage_fn stage_kernel(const cfd2d_fvm* h, int stage) {
+    switch (h->stage_nt) {
+        case 128: return stage_kernel_nt<128, 8>(h->ctrl.flux, h->ctrl.order, stage);
+        case 384: return stage_kernel_nt<384, 2>(h->ctrl.flux, h->ctrl.order, stage);
+        case 512: return stage_kernel_nt<512, 2>(h->ctrl.flux, h->ctrl.order, stage);
+        default:  return stage_kernel_nt<256, 4>(h->ctrl.flux, h->ctrl.order, stage);
+    }
+}
+
+// tiles: nullptr = all tiles [0, ntiles), else a list of n tile ids
+static void launch_stage(cfd2d_fvm* h, int stage, const int* tiles, int n) {
+    if (n <= 0) return;
+    KTimer t(h, stage == 1 ? CFD2D_K_STAGE1 : CFD2D_K_STAGE2);
+    FParams q = h->Q;
+    q.tile_ids = tiles;
+    stage_fn f = stage_kernel(h, stage);
+    if (stage == 1) f<<<n, h->stage_nt, h->stage_smem, h->stream>>>(h->P, q, h->W, h->Ua, h->Ub, h->Wb, h->G);
+    else            f<<<n, h->stage_nt, h->stage_smem, h->stream>>>(h->P, q, h->Wb, h->Ub, h->Ua, h->W, h->G);
+}
+
+// halo exchange of U4 (rec4 = 1) into `U`'s halo slice followed by the halo prim conversion into
+// `W`, or of G8 (rec4 = 2).  Method::exchange semantics (method.h:13-41): recv lands contiguously at
+// recvShift.
+static int exchange_U(cfd2d_fvm* h, double4* U, double4* W, cudaStream_t st) {
     if (!h->halo) return 0;
-    KTimer t(h, CFD2D_K_HALO);
-    int rc = halo_exchange(h->halo, U, 1, h->stream, &h->launches);
+    KTimer t(h, CFD2D_K_HALO, st);
+    int rc = halo_exchange(h->halo, U, 1, st, &h->launches);
     if (rc) { h->error = halo_error(h->halo); return rc; }
-    launch_prim(h, U, h->nc, h->nc_ex);
+    launch_prim(h, U, W, h->nc, h->nc_ex, st);
     return 0;
 }
 
-static int exchange_G(cfd2d_fvm* h) {
+static int exchange_G(cfd2d_fvm* h, cudaStream_t st) {
     if (!h->halo || h->ctrl.order != 2) return 0;
-    KTimer t(h, CFD2D_K_HALO);
-    int rc = halo_exchange(h->halo, h->G, 2, h->stream, &h->launches);
+    KTimer t(h, CFD2D_K_HALO, st);
+    int rc = halo_exchange(h->halo, h->G, 2, st, &h->launches);
     if (rc) h->error = halo_error(h->halo);
     return rc;
 }
 
-// One whole RK2 step = the body of the while loop of FVM_TVD::run (fvm_tvd.cpp:310-450).
-static int enqueue_step(cfd2d_fvm* h) {
+// One whole RK2 step = the body of the while loop of FVM_TVD::run (fvm_tvd.cpp:310-450), three
+// sweeps per stage (the layout of the reference; kept for the parity hooks and as the A/B twin of
+// the fused path: CFD2D_FUSED=0).
+static int enqueue_step_unfused(cfd2d_fvm* h) {
     int rc;
     if (h->ctrl.steady) launch_tau_steady(h);                 // :315
     // stage 1 (:323-374): W == prim(Ua) is valid on owned + halo cells here
-    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h))) return rc; }
+    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h, h->stream))) return rc; }
     launch_flux(h, h->Ua, 1);
     launch_update(h, 1);                                       // Ub, W
-    if ((rc = exchange_U(h, h->Ub))) return rc;
+    if ((rc = exchange_U(h, h->Ub, h->W, h->stream))) return rc;
     // stage 2 (:376-427) + half-sum + limits (:430-447)
-    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h))) return rc; }
+    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h, h->stream))) return rc; }
     launch_flux(h, h->Ub, 1);
     launch_update(h, 2);                                       // Ua, W, flags
-    if ((rc = exchange_U(h, h->Ua))) return rc;
+    if ((rc = exchange_U(h, h->Ua, h->W, h->stream))) return rc;
     launch_remediate(h);                                       // :449 (no-op kernel when nothing is flagged)
     return 0;
 }
+
+// The same step with one fused kernel per stage.  Serial handle: 3 launches per step.
+// Multi-rank handle: per stage, the comm stream computes the gradients of the cells a peer needs
+// (k_grad on the send list), exchanges them, and later exchanges the new state, while the compute
+// stream runs the INTERIOR tiles (no rank-halo data within two rings); the BOUNDARY tiles wait for
+// the gradient exchange.  W is ping-ponged: stage 1 reads W writes Wb, stage 2 reads Wb writes W.
+static int enqueue_step_fused(cfd2d_fvm* h) {
+    int rc;
+    if (h->ctrl.steady) launch_tau_steady(h);
+    if (!h->halo) {
+        launch_stage(h, 1, nullptr, h->ntiles);
+        launch_stage(h, 2, nullptr, h->ntiles);
+        launch_remediate(h);
+        return 0;
+    }
+    for (int stage = 1; stage <= 2; stage++) {
+        const double4* Wcur = stage == 1 ? h->W : h->Wb;
+        double4* Uout = stage == 1 ? h->Ub : h->Ua;
+        double4* Wout = stage == 1 ? h->Wb : h->W;
+        // comm stream: everything before this point on the compute stream (previous stage, its
+        // exchange) is complete
+        cudaEventRecord(h->ev_stage, h->stream);
+        cudaStreamWaitEvent(h->comm, h->ev_stage, 0);
+        if (h->ctrl.order == 2) {
+            if (h->n_send > 0) {
+                h->launches++;
+                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, Wcur, h->G, h->d_send_dev, h->n_send);
+            }
+            if ((rc = exchange_G(h, h->comm))) return rc;
+        }
+        cudaEventRecord(h->ev_G, h->comm);
+        launch_stage(h, stage, h->d_interior, h->n_interior);
+        cudaStreamWaitEvent(h->stream, h->ev_G, 0);
+        launch_stage(h, stage, h->d_boundary, h->n_boundary);
+        // new state of the send cells -> peers; the next stage's interior tiles do not need it
+        cudaEventRecord(h->ev_stage, h->stream);
+        cudaStreamWaitEvent(h->comm, h->ev_stage, 0);
+        if ((rc = exchange_U(h, Uout, Wout, h->comm))) return rc;
+        cudaEventRecord(h->ev_U, h->comm);
+        if (stage == 2) {
+            // remediateLimCells reads neighbour states, possibly halo cells: after the exchange
+            cudaStreamWaitEvent(h->stream, h->ev_U, 0);
+            launch_remediate(h);
+        }
+    }
+    // the next step's comm work is ordered after ev_U by the comm stream itself; its boundary tiles
+    // wait on ev_G, recorded after it
+    return 0;
+}
+
+static int enqueue_step(cfd2d_fvm* h) { return h->fused ? enqueue_step_fused(h) : enqueue_step_unfused(h); }
 
 static void drop_graph(cfd2d_fvm* h) {
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -269,6 +372,14 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete h; return CFD2D_ECUDA; }
         cudaEventCreate(&h->ev0); cudaEventCreate(&h->ev1);
     }
+    // ---- device cell numbering: owned cells along a Hilbert curve (fvm_tiling.h); everything below
+    // is built from the renumbered mesh `pm`; the caller's numbering only reappears in set/get_state,
+    // the parity hooks and the sweep order of remediateLimCells.  Edge ids stay the caller's.
+    bool hilbert = true;
+    if (const char* ev = getenv("CFD2D_HILBERT")) hilbert = atoi(ev) != 0;
+    hilbert_cell_order(nc, nc_ex, m->cell_cx, m->cell_cy, hilbert, h->perm, h->orig);
+    HostMesh pm;
+    permute_mesh(m, h->perm, h->orig, pm);
     // ---- internal edge order.  The flux kernel may visit edges in any order (each edge is independent,
     // F is addressed through the per-cell slot table, whose SLOT order -- the summation order -- is
     // untouched).  Edges are grouped by the direction of their normal (16 bins over [0, pi)), inner
@@ -290,9 +401,9 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         std::vector<int> key(ne);
         for (int e = 0; e < ne; e++) {
             int b;
-            if (m->edge_c2[e] < 0) b = NBIN;                      // boundary edges: own group, last
+            if (pm.edge_c2[e] < 0) b = NBIN;                      // boundary edges: own group, last
             else {
-                double a = atan2(m->edge_ny[e], m->edge_nx[e]);   // (-pi, pi]
+                double a = atan2(pm.edge_ny[e], pm.edge_nx[e]);   // (-pi, pi]
                 if (a < 0) a += PI_;                              // fold n and -n together
                 b = (int)floor((a + PI_ / (2 * NBIN)) / (PI_ / NBIN));
                 if (b >= NBIN || b < 0) b = 0;
@@ -316,23 +427,23 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     std::vector<double> s_nx(3 * (size_t)nc), s_ny(3 * (size_t)nc), s_l(3 * (size_t)nc);
     for (int cc = 0; cc < nc; cc++) {
         for (int k = 0; k < 3; k++) {
-            int e = m->cell_edges[3 * (size_t)cc + k];
+            int e = pm.cell_edges[3 * (size_t)cc + k];
             if (e < 0 || e >= ne) { g_create_error = "cell_edges entry out of range"; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
             size_t o = (size_t)k * nc + cc;
-            if (m->edge_c1[e] == cc) {
-                s_nb[o] = m->edge_c2[e] >= 0 ? m->edge_c2[e] : -1 - m->edge_bc[e];
-                s_nx[o] = m->edge_nx[e]; s_ny[o] = m->edge_ny[e];
+            if (pm.edge_c1[e] == cc) {
+                s_nb[o] = pm.edge_c2[e] >= 0 ? pm.edge_c2[e] : -1 - pm.edge_bc[e];
+                s_nx[o] = pm.edge_nx[e]; s_ny[o] = pm.edge_ny[e];
                 s_es[o] = epos[e] * 2;
-            } else if (m->edge_c2[e] == cc) {
-                s_nb[o] = m->edge_c1[e];
-                s_nx[o] = -m->edge_nx[e]; s_ny[o] = -m->edge_ny[e];
+            } else if (pm.edge_c2[e] == cc) {
+                s_nb[o] = pm.edge_c1[e];
+                s_nx[o] = -pm.edge_nx[e]; s_ny[o] = -pm.edge_ny[e];
                 s_es[o] = epos[e] * 2 + 1;
             } else {
                 g_create_error = "cell_edges names an edge that does not touch the cell";
                 cfd2d_fvm_destroy(h);
                 return CFD2D_EINVAL;
             }
-            s_l[o] = m->edge_l[e];
+            s_l[o] = pm.edge_l[e];
         }
     }
     // ---- per edge tables
@@ -343,15 +454,15 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     std::vector<int> ebc(ne);
     for (int q = 0; q < ne; q++) {
         const int e = order[q];                                       // caller's edge id
-        int c1 = m->edge_c1[e], c2 = m->edge_c2[e];
+        int c1 = pm.edge_c1[e], c2 = pm.edge_c2[e];
         e_c[q] = make_int2(c1, c2);
-        e_n[q] = make_double2(m->edge_nx[e], m->edge_ny[e]);
-        e_l2[q] = m->edge_l[e] * 0.5;                                 // fvm_tvd.cpp:335
-        ebc[q] = m->edge_bc[e];
-        const double* g = m->edge_gp + 4 * (size_t)e;
+        e_n[q] = make_double2(pm.edge_nx[e], pm.edge_ny[e]);
+        e_l2[q] = pm.edge_l[e] * 0.5;                                 // fvm_tvd.cpp:335
+        ebc[q] = pm.edge_bc[e];
+        const double* g = pm.edge_gp.data() + 4 * (size_t)e;
         // DL = PE - P(cell) (fvm_tvd.cpp:661-664): the same subtraction, done once
-        e_d1[q] = make_double4(g[0] - m->cell_cx[c1], g[1] - m->cell_cy[c1], g[2] - m->cell_cx[c1], g[3] - m->cell_cy[c1]);
-        if (c2 >= 0) e_d2[q] = make_double4(g[0] - m->cell_cx[c2], g[1] - m->cell_cy[c2], g[2] - m->cell_cx[c2], g[3] - m->cell_cy[c2]);
+        e_d1[q] = make_double4(g[0] - pm.cell_cx[c1], g[1] - pm.cell_cy[c1], g[2] - pm.cell_cx[c1], g[3] - pm.cell_cy[c1]);
+        if (c2 >= 0) e_d2[q] = make_double4(g[0] - pm.cell_cx[c2], g[1] - pm.cell_cy[c2], g[2] - pm.cell_cx[c2], g[3] - pm.cell_cy[c2]);
         else e_d2[q] = make_double4(0, 0, 0, 0);
     }
     std::vector<MatC> mats(p->nmat);
@@ -364,10 +475,10 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         mats[i] = q;
     }
     std::vector<unsigned char> cmat(nc_ex);
-    for (int i = 0; i < nc_ex; i++) cmat[i] = (unsigned char)m->cell_mat[i];
+    for (int i = 0; i < nc_ex; i++) cmat[i] = (unsigned char)pm.cell_mat[i];
     std::vector<int> bkind(p->bc_kind, p->bc_kind + p->nbc);
     std::vector<double> bpar(p->bc_par, p->bc_par + 4 * (size_t)p->nbc);
-    std::vector<double> cS(m->cell_S, m->cell_S + nc_ex);
+    const std::vector<double>& cS = pm.cell_S;
 
     KParams& P = h->P;
     P.nc = nc; P.nc_ex = nc_ex; P.ne = ne; P.nmat = p->nmat;
@@ -403,6 +514,10 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     TRY(dev_alloc(h, &h->Ua, (size_t)nc_ex));
     TRY(dev_alloc(h, &h->Ub, (size_t)nc_ex));
     TRY(dev_alloc(h, &h->W, (size_t)nc_ex));
+    TRY(dev_alloc(h, &h->Wb, (size_t)nc_ex));
+    TRY(dev_alloc(h, &h->io_u32, (size_t)nc));
+    TRY(dev_upload(h, &P.c_perm, h->perm));
+    TRY(dev_upload(h, &P.c_orig, h->orig));
     TRY(dev_alloc(h, &h->G, 2 * (size_t)(nc_ex ? nc_ex : 1)));
     TRY(dev_alloc(h, &h->F, (size_t)ne));
     for (int i = 0; i < 6; i++) TRY(dev_alloc(h, &h->io[i], (size_t)nc));
@@ -412,14 +527,97 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     cudaMemset(h->Ua, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
     cudaMemset(h->Ub, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
     cudaMemset(h->W, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
+    cudaMemset(h->Wb, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
     cudaMemset(h->G, 0, 2 * (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
     cudaMemset(P.cfl, 0, (size_t)(nc ? nc : 1) * sizeof(double));
     cudaMemset(P.ctau, 0, (size_t)(nc ? nc : 1) * sizeof(double));
+    // ---- tile plan of the fused stage kernel
+    // Default layout: three sweeps per stage.  Measured on B200 at 4 M cells (profiles/README.md) the
+    // fused kernel moves ~35 % fewer HBM bytes but its barrier-separated phases expose more load
+    // latency than the three full-width sweeps hide; it stays selectable (cfd2d_fvm_use_fused,
+    // CFD2D_FUSED=1) and is held to bit-identity with the sweeps by the tests.
+    h->fused = false;
+    if (const char* ev = getenv("CFD2D_FUSED")) h->fused = atoi(ev) != 0;
+    {
+        int TC = 768;
+        if (const char* ev = getenv("CFD2D_TILE")) TC = atoi(ev);
+        h->stage_nt = 512;
+        if (const char* ev = getenv("CFD2D_NT")) h->stage_nt = atoi(ev);
+        if (h->stage_nt != 128 && h->stage_nt != 256 && h->stage_nt != 384 && h->stage_nt != 512) h->stage_nt = 256;
+        TilePlan tp;
+        std::string terr = build_tile_plan(pm, TC, tp);
+        if (!terr.empty()) { g_create_error = terr; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
+        h->ntiles = tp.ntiles;
+        h->n_interior = (int)tp.interior.size();
+        h->n_boundary = (int)tp.boundary.size();
+        const size_t net = tp.e_c1.size();
+        std::vector<double2> t_n(net);
+        std::vector<double> t_l2(net);
+        std::vector<double4> t_d1(net), t_d2(net);
+        for (size_t q = 0; q < net; q++) {
+            const int e = tp.e_id[q];
+            const int c1 = pm.edge_c1[e], c2 = pm.edge_c2[e];
+            t_n[q] = make_double2(pm.edge_nx[e], pm.edge_ny[e]);
+            t_l2[q] = pm.edge_l[e] * 0.5;                               // fvm_tvd.cpp:335
+            const double* g = pm.edge_gp.data() + 4 * (size_t)e;
+            t_d1[q] = make_double4(g[0] - pm.cell_cx[c1], g[1] - pm.cell_cy[c1], g[2] - pm.cell_cx[c1], g[3] - pm.cell_cy[c1]);
+            if (c2 >= 0) t_d2[q] = make_double4(g[0] - pm.cell_cx[c2], g[1] - pm.cell_cy[c2], g[2] - pm.cell_cx[c2], g[3] - pm.cell_cy[c2]);
+            else t_d2[q] = make_double4(0, 0, 0, 0);
+        }
+        FParams& Q = h->Q;
+        Q.tile_ids = nullptr;
+        Q.nl_max = tp.nl_max; Q.ne_max = tp.ne_max;
+        TRY(dev_upload(h, &Q.tiles, tp.tiles));
+        TRY(dev_upload(h, &Q.ring, tp.ring));
+        TRY(dev_upload(h, &Q.g_nb, tp.g_nb));
+        TRY(dev_upload(h, &Q.g_nx, tp.g_nx));
+        TRY(dev_upload(h, &Q.g_ny, tp.g_ny));
+        TRY(dev_upload(h, &Q.g_l, tp.g_l));
+        TRY(dev_upload(h, &Q.e_c1, tp.e_c1));
+        TRY(dev_upload(h, &Q.e_c2, tp.e_c2));
+        TRY(dev_upload(h, &Q.e_cl, tp.e_cl));
+        TRY(dev_upload(h, &Q.e_n, t_n));
+        TRY(dev_upload(h, &Q.e_l2, t_l2));
+        TRY(dev_upload(h, &Q.e_d1, t_d1));
+        TRY(dev_upload(h, &Q.e_d2, t_d2));
+        TRY(dev_upload(h, &Q.u_es, tp.u_es));
+        Q.c_orig = P.c_orig;
+        { const int* q = nullptr; TRY(dev_upload(h, &q, tp.interior)); h->d_interior = (int*)q; }
+        { const int* q = nullptr; TRY(dev_upload(h, &q, tp.boundary)); h->d_boundary = (int*)q; }
+        h->stage_smem = ((c->order == 2 ? 4 * (size_t)tp.nl_max : 0) + 2 * (size_t)tp.ne_max) * sizeof(double2);
+        if (h->stage_smem > 227 * 1024) { g_create_error = "tile does not fit in shared memory (lower CFD2D_TILE)"; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
+        for (int st = 1; st <= 2; st++) {
+            stage_fn f = stage_kernel(h, st);
+            CUDA_TRY(h, cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stage_smem));
+        }
+        char b[256];
+        snprintf(b, sizeof b, "tiles=%d (TC=%d, interior=%d, boundary=%d) nl_max=%d ne_max=%d smem=%zu B ring/own=%.3f edges/own=%.3f nt=%d",
+                 tp.ntiles, tp.TC, h->n_interior, h->n_boundary, tp.nl_max, tp.ne_max, h->stage_smem,
+                 nc ? (double)tp.sum_ring / nc : 0.0, nc ? (double)tp.sum_ne / nc : 0.0, h->stage_nt);
+        h->plan_summary = b;
+    }
     if (halo && halo->nranks > 1) {
         std::string herr;
-        h->halo = halo_create(halo, nc, nc_ex, device, &herr);
+        // the send lists name the caller's cells: translate to device ids
+        int nsend = 0;
+        for (int r = 0; r < halo->nranks; r++) nsend += halo->send_count[r];
+        std::vector<int> send_dev(nsend > 0 ? nsend : 1, 0);
+        for (int i = 0; i < nsend; i++) {
+            int s = halo->send_ind[i];
+            if (s < 0 || s >= nc) { g_create_error = "send_ind entry is not an owned cell"; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
+            send_dev[i] = h->perm[s];
+        }
+        cfd2d_halo hd = *halo;
+        hd.send_ind = send_dev.data();
+        h->halo = halo_create(&hd, nc, nc_ex, device, &herr);
         if (!h->halo) { g_create_error = herr; cfd2d_fvm_destroy(h); return CFD2D_ENCCL; }
         h->use_graph = false;   // NCCL point-to-point is enqueued directly
+        h->n_send = nsend;
+        { const int* q = nullptr; TRY(dev_upload(h, &q, send_dev)); h->d_send_dev = (int*)q; }
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_G, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_U, cudaEventDisableTiming));
     }
     CUDA_TRY(h, cudaDeviceSynchronize());
 #undef TRY
@@ -436,6 +634,10 @@ void cfd2d_fvm_destroy(cfd2d_fvm* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->ev_G) cudaEventDestroy(h->ev_G);
+    if (h->ev_stage) cudaEventDestroy(h->ev_stage);
+    if (h->ev_U) cudaEventDestroy(h->ev_U);
+    if (h->comm) { cudaStreamSynchronize(h->comm); cudaStreamDestroy(h->comm); }
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -458,6 +660,76 @@ int cfd2d_fvm_use_graph(cfd2d_fvm* h, int on) {
     return 0;
 }
 
+int cfd2d_fvm_use_fused(cfd2d_fvm* h, int on) {
+    if (!h) return CFD2D_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm) cudaStreamSynchronize(h->comm);
+    drop_graph(h);
+    h->fused = on != 0;
+    return 0;
+}
+
+const char* cfd2d_fvm_plan_summary(const cfd2d_fvm* h) { return h ? h->plan_summary.c_str() : ""; }
+
+int cfd2d_tiling_plan(const cfd2d_mesh* m, int tile_cells, int hilbert, int32_t* perm_out, int64_t* stats_out) {
+    g_create_error.clear();
+    if (!m || m->nc < 0 || m->nc_ex < m->nc || m->ne < 0) { g_create_error = "bad mesh"; return CFD2D_EINVAL; }
+    std::vector<int> perm, orig;
+    hilbert_cell_order(m->nc, m->nc_ex, m->cell_cx, m->cell_cy, hilbert != 0, perm, orig);
+    HostMesh pm;
+    permute_mesh(m, perm, orig, pm);
+    TilePlan tp;
+    std::string err = build_tile_plan(pm, tile_cells, tp);
+    if (!err.empty()) { g_create_error = err; return CFD2D_EINVAL; }
+    // ---- invariants the kernel relies on
+    for (int t = 0; t < tp.ntiles && err.empty(); t++) {
+        const TileInfo& ti = tp.tiles[t];
+        auto gid = [&](int l) { return l < ti.n_own ? ti.cbeg + l : tp.ring[ti.roff + l - ti.n_own]; };
+        for (int q = 0; q < ti.ne_t; q++) {
+            size_t eo = (size_t)ti.eoff + q;
+            int e = tp.e_id[eo];
+            int l1 = (int)(tp.e_cl[eo] & 0xffffu), l2 = (int)(tp.e_cl[eo] >> 16);
+            if (l1 >= ti.n_l || gid(l1) != pm.edge_c1[e] || tp.e_c1[eo] != pm.edge_c1[e]) { err = "edge c1 local/global id mismatch"; break; }
+            if (pm.edge_c2[e] >= 0) {
+                if (l2 >= ti.n_l || gid(l2) != pm.edge_c2[e] || tp.e_c2[eo] != pm.edge_c2[e]) { err = "edge c2 local/global id mismatch"; break; }
+            } else if (tp.e_c2[eo] != -1 - pm.edge_bc[e]) { err = "boundary code mismatch"; break; }
+        }
+        for (int j = 0; j < ti.n_own && err.empty(); j++) {
+            int c = ti.cbeg + j;
+            for (int k = 0; k < 3; k++) {
+                int es = tp.u_es[(size_t)k * pm.nc + c];
+                int q = es >> 1;
+                if (q < 0 || q >= ti.ne_t) { err = "u_es out of the tile's edge range"; break; }
+                int e = tp.e_id[(size_t)ti.eoff + q];
+                if (e != pm.cell_edges[3 * (size_t)c + k]) { err = "u_es names the wrong edge"; break; }
+                if (((es & 1) ? pm.edge_c2[e] : pm.edge_c1[e]) != c) { err = "u_es side bit wrong"; break; }
+            }
+        }
+        for (int j = 0; j < ti.n_g && err.empty(); j++) {
+            int c = gid(j);
+            if (c < 0 || c >= pm.nc) { err = "gradient computed for a non-owned cell"; break; }
+            for (int k = 0; k < 3; k++) {
+                int e = pm.cell_edges[3 * (size_t)c + k];
+                int nb = tp.g_nb[(size_t)ti.goff + (size_t)k * ti.gstride + j];
+                int want = pm.edge_c1[e] == c ? pm.edge_c2[e] : pm.edge_c1[e];
+                if (want < 0) want = -1 - pm.edge_bc[e];
+                if (nb != want) { err = "gradient table neighbour mismatch"; break; }
+            }
+        }
+        for (int j = ti.n_g; j < ti.n_l && err.empty(); j++)
+            if (gid(j) < pm.nc) err = "computable ring-1 cell listed as halo";
+    }
+    if (!err.empty()) { g_create_error = "tile plan invariant violated: " + err; return CFD2D_EINVAL; }
+    if (perm_out) for (int i = 0; i < m->nc_ex; i++) perm_out[i] = perm[i];
+    if (stats_out) {
+        stats_out[0] = tp.ntiles; stats_out[1] = tp.nl_max; stats_out[2] = tp.ne_max; stats_out[3] = tp.sum_ng;
+        stats_out[4] = tp.sum_ne; stats_out[5] = tp.sum_ring; stats_out[6] = (int64_t)tp.interior.size();
+        stats_out[7] = (int64_t)tp.boundary.size();
+    }
+    return 0;
+}
+
 int cfd2d_fvm_set_state(cfd2d_fvm* h, const double* ro, const double* ru, const double* rv, const double* re,
                         const uint32_t* flag) {
     if (!h || !ro || !ru || !rv || !re) return CFD2D_EINVAL;
@@ -465,14 +737,17 @@ int cfd2d_fvm_set_state(cfd2d_fvm* h, const double* ro, const double* ru, const 
     size_t n = (size_t)h->nc * sizeof(double);
     const double* src[4] = {ro, ru, rv, re};
     for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaMemcpyAsync(h->io[i], src[i], n, cudaMemcpyHostToDevice, h->stream));
-    if (flag) CUDA_TRY(h, cudaMemcpyAsync(h->P.flag, flag, (size_t)h->nc * 4, cudaMemcpyHostToDevice, h->stream));
-    else CUDA_TRY(h, cudaMemsetAsync(h->P.flag, 0, (size_t)(h->nc ? h->nc : 1) * 4, h->stream));
+    if (flag && h->nc) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->io_u32, flag, (size_t)h->nc * 4, cudaMemcpyHostToDevice, h->stream));
+        h->launches++;
+        k_scatter_perm<uint32_t><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->io_u32, h->P.flag);
+    } else CUDA_TRY(h, cudaMemsetAsync(h->P.flag, 0, (size_t)(h->nc ? h->nc : 1) * 4, h->stream));
     if (h->nc) {
         h->launches++;
-        k_pack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->io[0], h->io[1], h->io[2], h->io[3], h->Ua);
+        k_pack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->io[0], h->io[1], h->io[2], h->io[3], h->Ua);
     }
-    launch_prim(h, h->Ua, 0, h->nc);
-    int rc = exchange_U(h, h->Ua);
+    launch_prim(h, h->Ua, h->W, 0, h->nc, h->stream);
+    int rc = exchange_U(h, h->Ua, h->W, h->stream);
     if (rc) return rc;
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
@@ -526,7 +801,7 @@ int cfd2d_fvm_step_async(cfd2d_fvm* h, int nsteps) {
             CUDA_TRY(h, e);
             CUDA_TRY(h, cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
         }
-        int per_step = 3 + 2 * (h->ctrl.order == 2 ? 2 : 1) + (h->ctrl.steady ? 1 : 0);
+        int per_step = (h->fused ? 3 : 3 + 2 * (h->ctrl.order == 2 ? 2 : 1)) + (h->ctrl.steady ? 1 : 0);
         for (int s = 0; s < nsteps; s++) {
             CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
             h->launches += per_step;
@@ -561,12 +836,20 @@ int cfd2d_fvm_get_state(cfd2d_fvm* h, double* ro, double* ru, double* rv, double
     size_t n = (size_t)h->nc * sizeof(double);
     if (h->nc) {
         h->launches++;
-        k_unpack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->Ua, h->io[0], h->io[1], h->io[2], h->io[3]);
+        k_unpack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->Ua, h->io[0], h->io[1], h->io[2], h->io[3]);
     }
     double* dst[4] = {ro, ru, rv, re};
     for (int i = 0; i < 4; i++) CUDA_TRY(h, cudaMemcpyAsync(dst[i], h->io[i], n, cudaMemcpyDeviceToHost, h->stream));
-    if (cTau) CUDA_TRY(h, cudaMemcpyAsync(cTau, h->P.ctau, n, cudaMemcpyDeviceToHost, h->stream));
-    if (flag) CUDA_TRY(h, cudaMemcpyAsync(flag, h->P.flag, (size_t)h->nc * 4, cudaMemcpyDeviceToHost, h->stream));
+    if (cTau && h->nc) {
+        h->launches++;
+        k_gather_perm<double><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->P.ctau, h->io[4]);
+        CUDA_TRY(h, cudaMemcpyAsync(cTau, h->io[4], n, cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (flag && h->nc) {
+        h->launches++;
+        k_gather_perm<uint32_t><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->P.flag, h->io_u32);
+        CUDA_TRY(h, cudaMemcpyAsync(flag, h->io_u32, (size_t)h->nc * 4, cudaMemcpyDeviceToHost, h->stream));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -599,7 +882,7 @@ int cfd2d_fvm_calc_grad(cfd2d_fvm* h, double* grad8) {
     launch_grad(h);
     double* tmp = nullptr;
     CUDA_TRY(h, cudaMalloc(&tmp, (size_t)(h->nc ? h->nc : 1) * 64));
-    if (h->nc) k_unpack_grad<<<nblk(2 * (long long)h->nc, 256), 256, 0, h->stream>>>(h->nc, h->G, tmp);
+    if (h->nc) k_unpack_grad<<<nblk(2 * (long long)h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->G, tmp);
     cudaError_t e = cudaMemcpyAsync(grad8, tmp, (size_t)h->nc * 64, cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
     cudaFree(tmp);
@@ -612,7 +895,7 @@ int cfd2d_fvm_edge_fluxes(cfd2d_fvm* h, double* flux4) {
     if (!h || !flux4) return CFD2D_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc;
-    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h))) return rc; }
+    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h, h->stream))) return rc; }
     launch_flux(h, h->Ua, 0);
     std::vector<double> tmp(4 * (size_t)h->ne);
     CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), h->F, (size_t)h->ne * 32, cudaMemcpyDeviceToHost, h->stream));

@@ -41,8 +41,12 @@ struct KParams {
     double* ctau;           // cTau
     unsigned int* flag;
     int* err;               // [0] Newton-cap hits  [1] flagged-cell count  [2] Newton iterations (KAT)
-    int* lim_list;          // compacted flagged cells (unordered until sorted)
+    int* lim_list;          // compacted flagged cells, CALLER ids (unordered until sorted)
     int lim_cap;                         // power of two >= nc
+    // cell numbering: the device numbers owned cells along a Hilbert curve (fvm_tiling.h); the
+    // caller's numbering only matters for I/O and for the sweep order of remediateLimCells
+    const int* c_perm;      // [nc_ex] caller -> device
+    const int* c_orig;      // [nc_ex] device -> caller
 };
 
 __device__ __forceinline__ double4 ld4(const double4* __restrict__ p, int i) {
@@ -133,9 +137,12 @@ __global__ void __launch_bounds__(256) k_tau_fill(KParams P, double tau) {
 // -- ((pL+pR)/2 * n.x) * l with the edge's own normal, "+=" on the c1 side and "-=" on the c2 side
 // (the outward normal s*n reproduces the sign exactly) -- then the true division by S.  No atomics.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G) {
+// `list` (optional): only these n cells (multi-GPU: the cells whose gradients are sent to a peer).
+__global__ void __launch_bounds__(256) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G,
+                                              const int* __restrict__ list, int n) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.nc) return;
+    if (c >= n) return;
+    if (list) c = __ldg(list + c);
     double4 ws = ld4(W, c);
     double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
@@ -267,7 +274,7 @@ __global__ void __launch_bounds__(256) k_update(KParams P, const double4* __rest
         if (STAGE == 1) st4(Uout, c, ld4cg(Uin, c));
         else {
             int pos = atomicAdd(P.err + 1, 1);
-            if (pos < P.lim_cap) P.lim_list[pos] = c;
+            if (pos < P.lim_cap) P.lim_list[pos] = __ldg(P.c_orig + c);
         }
         return;
     }
@@ -296,14 +303,14 @@ __global__ void __launch_bounds__(256) k_update(KParams P, const double4* __rest
         if (lim) {
             P.flag[c] = fl | 2u;         // setCellFlagLim
             int pos = atomicAdd(P.err + 1, 1);
-            if (pos < P.lim_cap) P.lim_list[pos] = c;
+            if (pos < P.lim_cap) P.lim_list[pos] = __ldg(P.c_orig + c);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------
 // K6: FVM_TVD::remediateLimCells (fvm_tvd.cpp:464-499).  Rare path.  One block: sort the flagged
-// list ascending (bitonic, in global memory), then thread 0 replays the reference's in-place,
+// list ascending by caller id (bitonic, in global memory), then thread 0 replays the reference's in-place,
 // ascending-cell-order sweep (the order matters when two flagged cells are neighbours).  Keeps the
 // reference's quirk: only edges[].c2 is averaged, i.e. the cell itself when it is the edge's c2.
 // ---------------------------------------------------------------------------------------------
@@ -331,7 +338,7 @@ __global__ void __launch_bounds__(1024) k_remediate(KParams P, double4* U, doubl
     }
     if (threadIdx.x == 0) {
         for (int q = 0; q < n; q++) {
-            int c = a[q];
+            int c = P.c_perm[a[q]];          // ascending CALLER id = the reference's sweep order
             double sRO = 0.0, sRU = 0.0, sRV = 0.0, sRE = 0.0, S = 0.0;
             for (int k = 0; k < 3; k++) {
                 int es = P.s_es[(size_t)k * P.nc + c];
@@ -358,44 +365,62 @@ __global__ void __launch_bounds__(1024) k_remediate(KParams P, double4* U, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
-// state import/export: the reference's four separate arrays <-> U4 records
+// state import/export: the reference's four separate arrays (caller numbering) <-> U4 records
+// (device numbering).  One thread per caller cell: the SoA side is coalesced, the record side moves
+// whole 32-byte sectors.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_pack_state(int n, const double* __restrict__ ro, const double* __restrict__ ru,
-                                                    const double* __restrict__ rv, const double* __restrict__ re,
-                                                    double4* __restrict__ U) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    st4(U, c, make_double4(ro[c], ru[c], rv[c], re[c]));
+__global__ void __launch_bounds__(256) k_pack_state(int n, const int* __restrict__ perm, const double* __restrict__ ro,
+                                                    const double* __restrict__ ru, const double* __restrict__ rv,
+                                                    const double* __restrict__ re, double4* __restrict__ U) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st4(U, __ldg(perm + i), make_double4(ro[i], ru[i], rv[i], re[i]));
 }
 
-__global__ void __launch_bounds__(256) k_unpack_state(int n, const double4* __restrict__ U, double* __restrict__ ro,
-                                                      double* __restrict__ ru, double* __restrict__ rv, double* __restrict__ re) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= n) return;
-    double4 u = ld4cg(U, c);
-    ro[c] = u.x; ru[c] = u.y; rv[c] = u.z; re[c] = u.w;
+__global__ void __launch_bounds__(256) k_unpack_state(int n, const int* __restrict__ perm, const double4* __restrict__ U,
+                                                      double* __restrict__ ro, double* __restrict__ ru,
+                                                      double* __restrict__ rv, double* __restrict__ re) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double4 u = ld4cg(U, __ldg(perm + i));
+    ro[i] = u.x; ru[i] = u.y; rv[i] = u.z; re[i] = u.w;
 }
 
-// K8: primitive fields for FVM_TVD::save (convertConsToPar per cell, fvm_tvd.cpp:529-572)
+// out[i] = in[perm[i]] (device -> caller order) and in[perm[i]] = src[i] (caller -> device order)
+template <class T>
+__global__ void __launch_bounds__(256) k_gather_perm(int n, const int* __restrict__ perm, const T* __restrict__ in, T* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[perm[i]];
+}
+template <class T>
+__global__ void __launch_bounds__(256) k_scatter_perm(int n, const int* __restrict__ perm, const T* __restrict__ src, T* __restrict__ dst) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[perm[i]] = src[i];
+}
+
+// K8: primitive fields for FVM_TVD::save (convertConsToPar per cell, fvm_tvd.cpp:529-572), caller order
 __global__ void __launch_bounds__(256) k_primitive_out(KParams P, const double4* __restrict__ U, double* r, double* p, double* T,
                                                        double* u, double* v, double* cz) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.nc) return;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nc) return;
+    int c = __ldg(P.c_perm + i);
     double4 q = ld4cg(U, c);
     MatC m = get_mat(P, c);
     Prim w = cons_to_prim(q.x, q.y, q.z, q.w, m.gm1);
-    if (r) r[c] = w.r;
-    if (p) p[c] = w.p;
-    if (T) T[c] = prim_T(w, m);
-    if (u) u[c] = w.u;
-    if (v) v[c] = w.v;
-    if (cz) cz[c] = prim_cz(w, m);
+    if (r) r[i] = w.r;
+    if (p) p[i] = w.p;
+    if (T) T[i] = prim_T(w, m);
+    if (u) u[i] = w.u;
+    if (v) v[i] = w.v;
+    if (cz) cz[i] = prim_cz(w, m);
 }
 
-__global__ void __launch_bounds__(256) k_unpack_grad(int n, const double4* __restrict__ G, double* __restrict__ out8) {
+// gradients of caller cell s (two double4 records) -> out8[s][8]
+__global__ void __launch_bounds__(256) k_unpack_grad(int n, const int* __restrict__ perm, const double4* __restrict__ G, double* __restrict__ out8) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 2 * n) return;
-    double4 g = ld4cg(G, i);
+    int s = i >> 1, k = i & 1;
+    double4 g = ld4cg(G, 2 * __ldg(perm + s) + k);
     out8[4 * (size_t)i + 0] = g.x; out8[4 * (size_t)i + 1] = g.y; out8[4 * (size_t)i + 2] = g.z; out8[4 * (size_t)i + 3] = g.w;
 }
 

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CFD2D_LIB") or os.path.join(HERE, "csrc", "libcfd2d_b200.so")   # env: kernel-variant sweeps only
 
 FLUX_GODUNOV, FLUX_LAX = 0, 1
-K_NAMES = ["grad", "flux", "update1", "update2", "remediate", "timestep", "halo"]
+K_NAMES = ["grad", "flux", "update1", "update2", "remediate", "timestep", "halo", "stage1", "stage2"]
 NKERNELS = len(K_NAMES)
 
 ERRORS = {0: "OK", -1: "EINVAL", -2: "ENODEV", -3: "ECUDA", -4: "ENEWTON", -5: "EBC", -6: "ENCCL"}
@@ -137,6 +137,10 @@ def load_library() -> C.CDLL:
     lib.cfd2d_fvm_launch_count.restype = C.c_int64
     lib.cfd2d_fvm_set_stream.argtypes = [H, C.c_void_p]
     lib.cfd2d_fvm_use_graph.argtypes = [H, C.c_int]
+    lib.cfd2d_fvm_use_fused.argtypes = [H, C.c_int]
+    lib.cfd2d_fvm_plan_summary.argtypes = [H]
+    lib.cfd2d_fvm_plan_summary.restype = C.c_char_p
+    lib.cfd2d_tiling_plan.argtypes = [C.POINTER(CMesh), C.c_int, C.c_int, _ip, C.POINTER(C.c_int64)]
     lib.cfd2d_fvm_last_error.argtypes = [H]
     lib.cfd2d_fvm_last_error.restype = C.c_char_p
     lib.cfd2d_version.restype = C.c_char_p
@@ -149,6 +153,7 @@ EXPORTS = [
     "cfd2d_fvm_step_async", "cfd2d_fvm_sync", "cfd2d_fvm_get_state", "cfd2d_fvm_get_primitive", "cfd2d_fvm_tau",
     "cfd2d_fvm_time", "cfd2d_fvm_calc_grad", "cfd2d_fvm_edge_fluxes", "cfd2d_kat_rim_orig", "cfd2d_kat_calc_flux",
     "cfd2d_fvm_profile", "cfd2d_fvm_launch_count", "cfd2d_fvm_set_stream", "cfd2d_fvm_use_graph",
+    "cfd2d_fvm_use_fused", "cfd2d_fvm_plan_summary", "cfd2d_tiling_plan",
     "cfd2d_fvm_last_error", "cfd2d_version",
 ]
 
@@ -267,6 +272,14 @@ class Solver:
     def use_graph(self, on: bool):
         self._chk(self.lib.cfd2d_fvm_use_graph(self.h, 1 if on else 0))
 
+    def use_fused(self, on: bool):
+        """True: one tile-fused kernel per RK stage; False (default): three sweeps per stage."""
+        self._chk(self.lib.cfd2d_fvm_use_fused(self.h, 1 if on else 0))
+
+    @property
+    def plan_summary(self) -> str:
+        return self.lib.cfd2d_fvm_plan_summary(self.h).decode()
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.cfd2d_fvm_destroy(self.h)
@@ -277,6 +290,21 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+
+def tiling_plan(m, t: _task.Task, tile_cells=512, hilbert=True, nc_owned=None):
+    """Host-only: the cell renumbering and tile-plan statistics create() would use (CPU test hook)."""
+    lib = load_library()
+    pk = Packed(m, t, nc_owned=nc_owned)
+    perm = np.empty(pk.nc_ex, np.int32)
+    stats = np.zeros(8, np.int64)
+    rc = lib.cfd2d_tiling_plan(C.byref(pk.mesh), int(tile_cells), 1 if hilbert else 0, perm.ctypes.data_as(_ip),
+                               stats.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc != 0:
+        msg = lib.cfd2d_fvm_last_error(None)
+        raise CFDError(rc, msg.decode() if msg else "")
+    keys = ("ntiles", "nl_max", "ne_max", "sum_ng", "sum_ne", "sum_ring", "interior", "boundary")
+    return perm, dict(zip(keys, (int(x) for x in stats)))
 
 
 def kat_rim_orig(in8, gam=1.4, max_newton=0, device=0):

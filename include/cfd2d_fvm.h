@@ -169,7 +169,9 @@ int cfd2d_kat_calc_flux(int device, int n, const double* in12, double gam, int f
 #define CFD2D_K_REMEDIATE 4   /* K6: remediateLimCells                                              */
 #define CFD2D_K_TIMESTEP  5   /* K1: steady local time step                                         */
 #define CFD2D_K_HALO      6   /* K7: halo pack + exchange                                           */
-#define CFD2D_NKERNELS    7
+#define CFD2D_K_STAGE1    7   /* K9: tile-fused RK stage 1 (gradients + fluxes + residual + update)  */
+#define CFD2D_K_STAGE2    8   /* K9: tile-fused RK stage 2 (+ half-sum + limit flags)                */
+#define CFD2D_NKERNELS    9
 int cfd2d_fvm_profile(cfd2d_fvm* h, int nsteps, double* ms, int64_t* launches);
 
 /* Kernel launches issued by this handle since create (the bench's gpu_launches claim).            */
@@ -180,6 +182,23 @@ int cfd2d_fvm_set_stream(cfd2d_fvm* h, void* cuda_stream);
 
 /* Enable/disable CUDA-graph replay of the step (default on).                                      */
 int cfd2d_fvm_use_graph(cfd2d_fvm* h, int on);
+
+/* Choose how the step is laid out on the device: 0 (default) = three sweeps per stage as in
+ * FVM_TVD::run (gradient, edge-flux and update kernels with HBM staging), 1 = one tile-fused
+ * kernel per RK stage (gradients and edge fluxes stay in shared memory; fewer HBM bytes, more
+ * exposed latency -- see profiles/README.md).  Both produce the same bits.                        */
+int cfd2d_fvm_use_fused(cfd2d_fvm* h, int on);
+
+/* One-line description of the tile plan of this handle (tiles, ring overhead, shared memory).     */
+const char* cfd2d_fvm_plan_summary(const cfd2d_fvm* h);
+
+/* Host-only test hook (no GPU needed): builds the cell renumbering and the tile plan create()
+ * would build for `mesh` and verifies its invariants (every cell slot finds its edge in the tile,
+ * local ids consistent, ring-1 closure).  perm_out[nc_ex] (may be NULL) = caller -> device cell
+ * id; stats_out[8] (may be NULL) = ntiles, nl_max, ne_max, sum n_g, sum ne_t, sum ring-1,
+ * interior tiles, boundary tiles.  Returns 0 or CFD2D_EINVAL (message via last_error(NULL)).      */
+int cfd2d_tiling_plan(const cfd2d_mesh* mesh, int tile_cells, int hilbert, int32_t* perm_out,
+                      int64_t* stats_out);
 
 /* Multi-rank bootstrap: a 128-byte ncclUniqueId created on one rank (ncclGetUniqueId); the caller
  * ships it to the other ranks (MPI_Bcast in the reference host, torch.distributed here) and every

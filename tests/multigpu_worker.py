@@ -13,6 +13,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
 def main():
+    os.environ.setdefault("CFD2D_TILE", "128")      # several interior + boundary tiles per rank on this small mesh
     import torch
     import torch.distributed as dist
     from cfd2d_b200 import cases, decomp, fvm

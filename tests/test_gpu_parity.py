@@ -122,6 +122,56 @@ def test_graph_and_eager_paths_are_bit_identical():
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("flux,order", [(0, 2), (0, 1), (1, 2), (1, 1)])
+@pytest.mark.parametrize("tile,nt,hilbert", [(32, 128, 1), (100, 256, 1), (512, 384, 0), (700, 512, 1)])
+def test_fused_stage_kernel_equals_three_sweeps_bitwise(flux, order, tile, nt, hilbert, monkeypatch):
+    """k_stage (gradients + fluxes in shared memory, Hilbert-ordered tiles, perimeter edges
+    evaluated by both neighbouring tiles) against k_grad + k_flux + k_update on the same handle
+    layout: same expressions, same operand order => the same bits, for every tile size / block
+    size / cell order, with limit flags tripping (remediation sweep in caller order) on the way."""
+    monkeypatch.setenv("CFD2D_TILE", str(tile))
+    monkeypatch.setenv("CFD2D_NT", str(nt))
+    monkeypatch.setenv("CFD2D_HILBERT", str(hilbert))
+    c = cases.channel(40, 24, jitter=0.2, shuffle=True, two_materials=True)
+    c.task.p_max = 1.03e5                               # below the initial peak: cells get flagged
+    st = c.smooth_state()
+    outs = []
+    for fused in (True, False):
+        s = fvm.Solver(c.mesh, c.task, flux, order)
+        s.use_fused(fused)
+        s.set_state(*st)
+        s.calc_time_step()
+        s.step(9)
+        s.step(4)
+        outs.append(s.get_state())
+        s.close()
+    assert (outs[0][5] != 0).any()                      # the remediation path was exercised
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
+def test_fused_steady_and_flag_io_roundtrip(monkeypatch):
+    monkeypatch.setenv("CFD2D_TILE", "64")
+    c = cases.channel(24, 12, jitter=0.2, shuffle=True)
+    c.task.steady = 1
+    st = c.smooth_state()
+    flag = np.zeros(c.mesh.nc, np.uint32)
+    flag[[3, 77, 300]] = 2                              # frozen cells given by the caller (caller ids)
+    outs = []
+    for fused in (True, False):
+        s = fvm.Solver(c.mesh, c.task)
+        s.use_fused(fused)
+        s.set_state(*st, flag=flag)
+        s.calc_time_step()
+        ro0 = s.get_state()
+        assert np.array_equal(ro0[5], flag) and np.array_equal(ro0[0], st[0])   # I/O permutation round trip
+        s.step(5)
+        outs.append(s.get_state())
+        s.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
 def test_run_to_run_determinism():
     c = cases.channel(64, 32, jitter=0.2, shuffle=True)
     st = c.smooth_state()
