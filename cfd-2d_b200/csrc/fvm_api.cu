@@ -33,6 +33,10 @@ struct cfd2d_fvm {
     int ntiles = 0, n_interior = 0, n_boundary = 0, stage_nt = 256;
     size_t stage_smem = 0;
     int *d_interior = nullptr, *d_boundary = nullptr;
+    bool overlap = true;          // multi-rank: halo exchange on the comm stream, overlapped with interior work
+    int ne_int = 0;               // device edges [0, ne_int) touch owned cells only; [ne_int, ne) touch a halo cell
+    int *d_cells_int = nullptr, *d_cells_bnd = nullptr;   // owned cells without / with a halo neighbour
+    int n_cells_int = 0, n_cells_bnd = 0;
     int* d_send_dev = nullptr;    // send cells (device ids), all peers
     int n_send = 0;
     cudaStream_t comm = nullptr;  // halo exchange stream (multi-rank handles)
@@ -44,6 +48,8 @@ struct cfd2d_fvm {
     int* err = nullptr;
     // graph
     bool use_graph = true;
+    int graph_launches = 0;       // kernel launches inside one captured step
+    int eager_steps = 0;          // steps enqueued without a graph (multi-rank: NCCL warms up eagerly first)
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t graph_exec = nullptr;
     // profiling
@@ -136,21 +142,27 @@ static void launch_prim(cfd2d_fvm* h, const double4* U, double4* W, int c0, int 
     k_prim<<<nblk(c1 - c0, 256), 256, 0, st>>>(h->P, U, W, c0, c1);
 }
 
-static void launch_grad(cfd2d_fvm* h) {
-    if (h->nc == 0) return;
-    KTimer t(h, CFD2D_K_GRAD);
-    k_grad<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->W, h->G, nullptr, h->nc);
+// list == nullptr: all owned cells
+static void launch_grad(cfd2d_fvm* h, const int* list = nullptr, int n = -1, cudaStream_t st = nullptr) {
+    if (!list) n = h->nc;
+    if (n <= 0) return;
+    if (!st) st = h->stream;
+    KTimer t(h, CFD2D_K_GRAD, st);
+    k_grad<<<nblk(n, 256), 256, 0, st>>>(h->P, h->W, h->G, list, n);
 }
 
-static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale) {
-    if (h->ne == 0) return;
-    KTimer t(h, CFD2D_K_FLUX);
-    dim3 g(nblk(2 * (long long)h->ne, 128)), b(128);   // one thread per (edge, Gauss point)
+// device edges [e0, e1); e1 < 0: all edges
+static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale, int e0 = 0, int e1 = -1, cudaStream_t st = nullptr) {
+    if (e1 < 0) e1 = h->ne;
+    if (e1 <= e0) return;
+    if (!st) st = h->stream;
+    KTimer t(h, CFD2D_K_FLUX, st);
+    dim3 g(nblk(2 * (long long)(e1 - e0), 128)), b(128);   // one thread per (edge, Gauss point)
     int fx = h->ctrl.flux, od = h->ctrl.order;
-    if (fx == CFD2D_FLUX_GODUNOV && od == 2) k_flux<0, 2><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
-    else if (fx == CFD2D_FLUX_GODUNOV) k_flux<0, 1><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
-    else if (od == 2) k_flux<1, 2><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
-    else k_flux<1, 1><<<g, b, 0, h->stream>>>(h->P, h->W, h->G, Ucur, h->F, scale);
+    if (fx == CFD2D_FLUX_GODUNOV && od == 2) k_flux<0, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
+    else if (fx == CFD2D_FLUX_GODUNOV) k_flux<0, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
+    else if (od == 2) k_flux<1, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
+    else k_flux<1, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
 }
 
 static void launch_update(cfd2d_fvm* h, int stage) {
@@ -225,21 +237,49 @@ static int exchange_G(cfd2d_fvm* h, cudaStream_t st) {
 }
 
 // One whole RK2 step = the body of the while loop of FVM_TVD::run (fvm_tvd.cpp:310-450), three
-// sweeps per stage (the layout of the reference; kept for the parity hooks and as the A/B twin of
-// the fused path: CFD2D_FUSED=0).
+// sweeps per stage (the layout of the reference).
+//
+// Multi-rank handles (two neighbour exchanges per stage).  Everything that touches halo
+// data -- the exchanges AND the small partition-boundary kernels -- runs on the high-priority comm
+// stream, concurrently with the interior sweeps on the compute stream:
+//   comm   : [exchange U of stage 1] grad(cells with a halo neighbour) | exchange G | flux(edges touching a halo cell)
+//   compute: grad(other cells) ......................................^ flux(interior edges) ............^ update
+// so the critical path of a stage is the same three sweeps as on one GPU.  The state exchange after
+// stage 2 is the only exposed one (remediateLimCells reads halo states).
 static int enqueue_step_unfused(cfd2d_fvm* h) {
     int rc;
+    const bool multi = h->halo != nullptr;
+    const bool ov = multi && h->overlap;
+    cudaStream_t S = h->stream, C = ov ? h->comm : h->stream;
+    const bool o2 = h->ctrl.order == 2;
     if (h->ctrl.steady) launch_tau_steady(h);                 // :315
-    // stage 1 (:323-374): W == prim(Ua) is valid on owned + halo cells here
-    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h, h->stream))) return rc; }
-    launch_flux(h, h->Ua, 1);
-    launch_update(h, 1);                                       // Ub, W
-    if ((rc = exchange_U(h, h->Ub, h->W, h->stream))) return rc;
-    // stage 2 (:376-427) + half-sum + limits (:430-447)
-    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h, h->stream))) return rc; }
-    launch_flux(h, h->Ub, 1);
-    launch_update(h, 2);                                       // Ua, W, flags
-    if ((rc = exchange_U(h, h->Ua, h->W, h->stream))) return rc;
+    for (int stage = 1; stage <= 2; stage++) {
+        double4* Ucur = stage == 1 ? h->Ua : h->Ub;          // state this stage starts from
+        if (!multi) {
+            if (o2) launch_grad(h);
+            launch_flux(h, Ucur, 1);
+        } else {
+            if (ov) { cudaEventRecord(h->ev_stage, S); cudaStreamWaitEvent(C, h->ev_stage, 0); }   // fork
+            if (stage == 2 && (rc = exchange_U(h, Ucur, h->W, C))) return rc;     // halo copy of the stage-1 result
+            if (o2) {
+                launch_grad(h, h->d_cells_bnd, h->n_cells_bnd, C);
+                if (ov) cudaEventRecord(h->ev_G, C);
+                if ((rc = exchange_G(h, C))) return rc;
+                launch_grad(h, h->d_cells_int, h->n_cells_int, S);
+                if (ov) cudaStreamWaitEvent(S, h->ev_G, 0);   // interior edges read the gradients of all owned cells
+            }
+            launch_flux(h, Ucur, 1, h->ne_int, h->ne, C);
+            if (ov) cudaEventRecord(h->ev_U, C);
+            launch_flux(h, Ucur, 1, 0, h->ne_int, S);
+            if (ov) cudaStreamWaitEvent(S, h->ev_U, 0);       // join
+        }
+        launch_update(h, stage);                               // stage 1: Ub, W; stage 2: Ua, W, flags (:366-374, :419-447)
+    }
+    if (multi) {
+        if (ov) { cudaEventRecord(h->ev_stage, S); cudaStreamWaitEvent(C, h->ev_stage, 0); }
+        if ((rc = exchange_U(h, h->Ua, h->W, C))) return rc;
+        if (ov) { cudaEventRecord(h->ev_U, C); cudaStreamWaitEvent(S, h->ev_U, 0); }
+    }
     launch_remediate(h);                                       // :449 (no-op kernel when nothing is flagged)
     return 0;
 }
@@ -410,15 +450,23 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
             }
             key[e] = b;
         }
-        if (EDGE_TILE <= 0) { for (int e = 0; e < ne; e++) { order[e] = e; epos[e] = e; } }
+        // multi-rank: edges that touch a halo cell go last (their flux waits for the halo exchange)
+        std::vector<int> ids;
+        ids.reserve(ne);
+        for (int e = 0; e < ne; e++) if (!(pm.edge_c1[e] >= nc || pm.edge_c2[e] >= nc)) ids.push_back(e);
+        h->ne_int = (int)ids.size();
+        for (int e = 0; e < ne; e++) if (pm.edge_c1[e] >= nc || pm.edge_c2[e] >= nc) ids.push_back(e);
+        if (EDGE_TILE <= 0) { for (int q = 0; q < ne; q++) { order[q] = ids[q]; epos[ids[q]] = q; } }
         else {
-            for (int t0 = 0; t0 < ne; t0 += EDGE_TILE) {
-                int t1 = t0 + EDGE_TILE < ne ? t0 + EDGE_TILE : ne;
-                int cnt[NBIN + 2] = {0};
-                for (int e = t0; e < t1; e++) cnt[key[e] + 1]++;
-                for (int b = 0; b <= NBIN; b++) cnt[b + 1] += cnt[b];
-                for (int e = t0; e < t1; e++) { int q = t0 + cnt[key[e]]++; order[q] = e; epos[e] = q; }
-            }
+            const int seg_beg[2] = {0, h->ne_int}, seg_end[2] = {h->ne_int, ne};
+            for (int sg = 0; sg < 2; sg++)
+                for (int t0 = seg_beg[sg]; t0 < seg_end[sg]; t0 += EDGE_TILE) {
+                    int t1 = t0 + EDGE_TILE < seg_end[sg] ? t0 + EDGE_TILE : seg_end[sg];
+                    int cnt[NBIN + 2] = {0};
+                    for (int i = t0; i < t1; i++) cnt[key[ids[i]] + 1]++;
+                    for (int b = 0; b <= NBIN; b++) cnt[b + 1] += cnt[b];
+                    for (int i = t0; i < t1; i++) { int e = ids[i]; int q = t0 + cnt[key[e]]++; order[q] = e; epos[e] = q; }
+                }
         }
     }
     h->edge_pos = epos;
@@ -611,10 +659,32 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         hd.send_ind = send_dev.data();
         h->halo = halo_create(&hd, nc, nc_ex, device, &herr);
         if (!h->halo) { g_create_error = herr; cfd2d_fvm_destroy(h); return CFD2D_ENCCL; }
-        h->use_graph = false;   // NCCL point-to-point is enqueued directly
+        // the step (both streams, fork/join through events, NCCL point-to-point included) is captured
+        // into one CUDA graph after two eager steps; CFD2D_GRAPH_MULTI=0 keeps it eager
+        h->use_graph = true;
+        if (const char* ev = getenv("CFD2D_GRAPH_MULTI")) h->use_graph = atoi(ev) != 0;
         h->n_send = nsend;
         { const int* q = nullptr; TRY(dev_upload(h, &q, send_dev)); h->d_send_dev = (int*)q; }
-        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->comm, cudaStreamNonBlocking));
+        // owned cells without / with a halo neighbour (gradient sweep split, enqueue_step_unfused)
+        std::vector<int> ci, cb;
+        for (int cc = 0; cc < nc; cc++) {
+            bool b = false;
+            for (int k = 0; k < 3; k++) {
+                int e = pm.cell_edges[3 * (size_t)cc + k];
+                int nb = pm.edge_c1[e] == cc ? pm.edge_c2[e] : pm.edge_c1[e];
+                if (nb >= nc) b = true;
+            }
+            (b ? cb : ci).push_back(cc);
+        }
+        h->n_cells_int = (int)ci.size(); h->n_cells_bnd = (int)cb.size();
+        { const int* q = nullptr; TRY(dev_upload(h, &q, ci)); h->d_cells_int = (int*)q; }
+        { const int* q = nullptr; TRY(dev_upload(h, &q, cb)); h->d_cells_bnd = (int*)q; }
+        if (const char* ev = getenv("CFD2D_OVERLAP")) h->overlap = atoi(ev) != 0;
+        {   // highest priority: the small pack / NCCL kernels must not queue behind a full-GPU sweep
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            CUDA_TRY(h, cudaStreamCreateWithPriority(&h->comm, cudaStreamNonBlocking, hi));
+        }
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_G, cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming));
         CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_U, cudaEventDisableTiming));
@@ -655,7 +725,7 @@ int cfd2d_fvm_set_stream(cfd2d_fvm* h, void* s) {
 
 int cfd2d_fvm_use_graph(cfd2d_fvm* h, int on) {
     if (!h) return CFD2D_EINVAL;
-    h->use_graph = on && !h->halo;
+    h->use_graph = on != 0;
     if (!h->use_graph) drop_graph(h);
     return 0;
 }
@@ -747,8 +817,12 @@ int cfd2d_fvm_set_state(cfd2d_fvm* h, const double* ro, const double* ru, const 
         k_pack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->io[0], h->io[1], h->io[2], h->io[3], h->Ua);
     }
     launch_prim(h, h->Ua, h->W, 0, h->nc, h->stream);
-    int rc = exchange_U(h, h->Ua, h->W, h->stream);
-    if (rc) return rc;
+    if (h->halo) {                                     // all NCCL traffic of a handle goes through its comm stream
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        int rc = exchange_U(h, h->Ua, h->W, h->comm);
+        if (rc) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(h->comm));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -790,24 +864,30 @@ int cfd2d_fvm_calc_time_step(cfd2d_fvm* h, double* tau_out) {
 int cfd2d_fvm_step_async(cfd2d_fvm* h, int nsteps) {
     if (!h || nsteps < 0) return CFD2D_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    int done = 0;
+    if (h->use_graph && !h->profiling && h->halo)
+        for (; done < nsteps && h->eager_steps < 2; done++, h->eager_steps++) {   // NCCL connections, lazy allocations
+            int rc = enqueue_step(h);
+            if (rc) return rc;
+        }
     if (h->use_graph && !h->profiling) {
-        if (!h->graph_exec) {
+        if (!h->graph_exec && done < nsteps) {
             int64_t l0 = h->launches;
             CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
             int rc = enqueue_step(h);
             cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
+            h->graph_launches = (int)(h->launches - l0);
             h->launches = l0;
             if (rc) return rc;
             CUDA_TRY(h, e);
             CUDA_TRY(h, cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
         }
-        int per_step = (h->fused ? 3 : 3 + 2 * (h->ctrl.order == 2 ? 2 : 1)) + (h->ctrl.steady ? 1 : 0);
-        for (int s = 0; s < nsteps; s++) {
+        for (int s = done; s < nsteps; s++) {
             CUDA_TRY(h, cudaGraphLaunch(h->graph_exec, h->stream));
-            h->launches += per_step;
+            h->launches += h->graph_launches;
         }
     } else {
-        for (int s = 0; s < nsteps; s++) {
+        for (int s = done; s < nsteps; s++) {
             int rc = enqueue_step(h);
             if (rc) return rc;
         }

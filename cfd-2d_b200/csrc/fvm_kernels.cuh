@@ -192,12 +192,14 @@ __global__ void __launch_bounds__(256) k_grad(KParams P, const double4* __restri
 template <int FLUX, int ORDER>
 __global__ void __launch_bounds__(128, FLUX == 0 ? CFD2D_FLUX_MINB : 8)
 k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
-       const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2) {
+       const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2, int e0, int e1) {
+    // edges [e0, e1) of the device edge order (multi-rank handles: interior edges first, edges that
+    // touch a halo cell last, so the halo exchange overlaps the interior sweep)
     int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int e = t >> 1;
+    int e = e0 + (t >> 1);
     const int gp = t & 1;
-    const bool live = e < P.ne;
-    if (!live) e = P.ne - 1;
+    const bool live = e < e1;
+    if (!live) e = e1 - 1;
     int2 cc = __ldg(P.e_c + e);
     double2 n = __ldg(P.e_n + e);
     double4 w1 = ld4(W, cc.x);

@@ -21,7 +21,13 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
-    for partition, flux, order, steady in (("metis", 0, 2, 0), ("slab", 1, 2, 0), ("metis", 1, 1, 0), ("slab", 0, 2, 1)):
+    # step layouts of a multi-rank handle: three sweeps with the halo exchange overlapped on the comm
+    # stream (default), the same serialised on one stream, and the tile-fused stage kernel
+    modes = {"overlap": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1"}, "serial": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "0"},
+             "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1"}}
+    cases_ = (("metis", 0, 2, 0), ("slab", 1, 2, 0), ("metis", 1, 1, 0), ("slab", 0, 2, 1))
+    for mode, partition, flux, order, steady in [(m,) + c for m in modes for c in cases_]:
+        os.environ.update(modes[mode])
         c = cases.channel(96, 48, jitter=0.2, shuffle=True)
         c.task.steady = steady
         st = c.smooth_state()
@@ -42,6 +48,7 @@ def main():
             dist.all_reduce(glob[k])
         s.close()
         if rank == 0:
+            os.environ["CFD2D_FUSED"] = "0"
             s1 = fvm.Solver(c.mesh, c.task, flux, order, device=local)
             s1.set_state(*st)
             tau1 = s1.calc_time_step()
@@ -49,7 +56,7 @@ def main():
             ref = s1.get_state()
             s1.close()
             same = all(np.array_equal(glob[k].cpu().numpy(), ref[k]) for k in range(4)) and tau == tau1
-            print(f"[multi-gpu x{world}] partition={partition} flux={flux} order={order} steady={steady}: "
+            print(f"[multi-gpu x{world}] mode={mode} partition={partition} flux={flux} order={order} steady={steady}: "
                   f"bitwise equal to 1 GPU = {same}, tau={tau}", flush=True)
             ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")

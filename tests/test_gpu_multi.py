@@ -27,4 +27,4 @@ def test_multi_gpu_equals_single_gpu_bitwise(n):
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0
-    assert r.stdout.count("bitwise equal to 1 GPU = True") == 4
+    assert r.stdout.count("bitwise equal to 1 GPU = True") == 12      # 3 step layouts x 4 cases
