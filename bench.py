@@ -57,7 +57,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -186,6 +186,7 @@ def workload_config(a):
     return {"workload": f"BASELINE configs[2]: synthetic {a.nx}x{a.ny}x2 = {2 * a.nx * a.ny} -cell triangulated channel per GPU, "
                         f"inlet/outlet/walls, smooth IC; RK2; order {a.order}; flux {a.flux}",
             "cells_per_gpu": 2 * a.nx * a.ny, "flux": a.flux, "order": a.order,
+            "partition": (a.partition if a.gpus > 1 else "none"),
             "l2_policy": "inputs larger than L2 (working set ~1.9 GB at 4 M cells vs 126 MB L2)"}
 
 
@@ -193,8 +194,8 @@ def workload_config(a):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)      # 200 timed steps after 20 warm-up
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--flux", default="godunov", choices=["godunov", "lax"])
     ap.add_argument("--order", type=int, default=2)
@@ -202,6 +203,8 @@ def main():
     ap.add_argument("--ny", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra Lax-Friedrichs variant lines")
+    ap.add_argument("--partition", default="slab", choices=["slab", "metis"],
+                    help="N>1: slab (default; O(N) setup) or the bundled METIS as the reference's Decomp (decomp.cpp:104)")
     ap.add_argument("--fused", action="store_true", help="one tile-fused kernel per stage (k_stage) instead of k_grad, k_flux, k_update")
     a = ap.parse_args()
     if a.impl == "reference":
@@ -230,7 +233,8 @@ def main():
         nc_local, nc_total = c.mesh.nc, c.mesh.nc
     else:
         from cfd2d_b200 import decomp
-        s, st, nc_local, nc_total = decomp.make_rank_solver(a.nx, a.ny, rank, world, local, flux, a.order, dist)
+        s, st, nc_local, nc_total = decomp.make_rank_solver(a.nx, a.ny, rank, world, local, flux, a.order, dist,
+                                                            partition=a.partition)
     if a.fused:
         s.use_fused(True)
     stream = torch.cuda.Stream()          # a real (capturable) stream; torch events are recorded on it
@@ -311,10 +315,18 @@ def main():
                                         "algorithmic_bytes_per_cell": ALGO_BYTES_KERNEL[dom[0]],
                                         "achieved": ach_dom, "frac": ach_dom / peak},
                     "per_kernel": per_kernel}
+    # measured DRAM traffic (ncu --set full capture of this command at 4 M cells, Godunov order 2; per launch)
     tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and nc_local == 4000000 and flux == 0 and a.order == 2:
         try:
-            roofline["traffic"] = json.load(open(tp)).get("stage_dram_bytes_4m")
+            tr = json.load(open(tp))
+            pk = tr["per_kernel_dram_bytes_4m"]
+            if fused:
+                roofline["traffic"] = 0.5 * (pk["stage1_fused"] + pk["stage2_fused"])
+            else:
+                roofline["traffic"] = tr["stage_dram_bytes_4m"]
+                roofline["dominant_kernel"]["traffic"] = pk.get(roofline["dominant_kernel"]["name"][2:])
+            roofline["traffic_source"] = tr["source"]
         except Exception:
             pass
 

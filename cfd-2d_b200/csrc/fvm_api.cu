@@ -587,7 +587,7 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     h->fused = false;
     if (const char* ev = getenv("CFD2D_FUSED")) h->fused = atoi(ev) != 0;
     {
-        int TC = 768;
+        int TC = 512;
         if (const char* ev = getenv("CFD2D_TILE")) TC = atoi(ev);
         h->stage_nt = 512;
         if (const char* ev = getenv("CFD2D_NT")) h->stage_nt = atoi(ev);
@@ -632,7 +632,8 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         Q.c_orig = P.c_orig;
         { const int* q = nullptr; TRY(dev_upload(h, &q, tp.interior)); h->d_interior = (int*)q; }
         { const int* q = nullptr; TRY(dev_upload(h, &q, tp.boundary)); h->d_boundary = (int*)q; }
-        h->stage_smem = ((c->order == 2 ? 4 * (size_t)tp.nl_max : 0) + 2 * (size_t)tp.ne_max) * sizeof(double2);
+        h->stage_smem = ((c->order == 2 ? 6 * (size_t)tp.nl_max : 2 * (size_t)tp.nl_max) + 2 * (size_t)tp.ne_max) * sizeof(double2)
+                        + (c->flux == CFD2D_FLUX_LAX ? (size_t)tp.nl_max * sizeof(double) : 0);
         if (h->stage_smem > 227 * 1024) { g_create_error = "tile does not fit in shared memory (lower CFD2D_TILE)"; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
         for (int st = 1; st <= 2; st++) {
             stage_fn f = stage_kernel(h, st);
@@ -763,7 +764,7 @@ int cfd2d_tiling_plan(const cfd2d_mesh* m, int tile_cells, int hilbert, int32_t*
             if (l1 >= ti.n_l || gid(l1) != pm.edge_c1[e] || tp.e_c1[eo] != pm.edge_c1[e]) { err = "edge c1 local/global id mismatch"; break; }
             if (pm.edge_c2[e] >= 0) {
                 if (l2 >= ti.n_l || gid(l2) != pm.edge_c2[e] || tp.e_c2[eo] != pm.edge_c2[e]) { err = "edge c2 local/global id mismatch"; break; }
-            } else if (tp.e_c2[eo] != -1 - pm.edge_bc[e]) { err = "boundary code mismatch"; break; }
+            } else if (tp.e_c2[eo] != -1 - pm.edge_bc[e] || l2 != 0xffff || l1 >= ti.n_own) { err = "boundary edge encoding mismatch"; break; }
         }
         for (int j = 0; j < ti.n_own && err.empty(); j++) {
             int c = ti.cbeg + j;

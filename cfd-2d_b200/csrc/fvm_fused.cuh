@@ -12,11 +12,14 @@
 // kernels (fvm_kernels.cuh), so fused and unfused states are bit-identical (tests/test_gpu_parity).
 //
 // Phases of a CTA (tile t):
+//   0. stage the primitive state W of the tile's cells and ring 1 in smem (one independent 32-byte
+//      load per thread: the memory-level parallelism of the kernel lives here); LF: also E = re/ro.
 //   1. gradients of the tile's cells and of the computable ring-1 cells -> smem (cell-parallel
-//      gather in Cell::edgesInd order, exactly k_grad); ring-1 cells that are rank-halo cells load
-//      the gradient received from their owner.
-//   2. edge fluxes: one thread per (edge, Gauss point) as in k_flux; W from HBM/L2 by global id,
-//      gradients from smem by local id; F*(l/2) -> smem.
+//      gather in Cell::edgesInd order, exactly k_grad; neighbours inside the tile from smem, ring
+//      1/2 from L2); ring-1 cells that are rank-halo cells load the gradient received from their
+//      owner.
+//   2. edge fluxes: one thread per (edge, Gauss point) as in k_flux; W and gradients from smem by
+//      local id, edge tables streamed coalesced; F*(l/2) -> smem.
 //   3. per owned cell: gather the three staged fluxes in slot order, RK update, new U and W.
 // W is double-buffered (other tiles still read the old W while this one writes the new one).
 #pragma once
@@ -40,23 +43,38 @@ __global__ void __launch_bounds__(NT, MINB)
 k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin, double4* Uout,
         double4* __restrict__ Wout, const double4* __restrict__ Gx) {
     extern __shared__ double2 smem[];
-    // gradients as four double2 planes (16-byte accesses of consecutive cells hit distinct banks)
-    double2* G0 = smem;
+    // all per-cell records as double2 planes (16-byte accesses of consecutive cells hit distinct banks)
+    double2* W0 = smem;                                   // {r, p} of the tile's cells + ring 1
+    double2* W1 = W0 + Q.nl_max;                          // {u, v}
+    double2* G0 = W1 + Q.nl_max;                          // gradients: {Rx,Ry} {Px,Py} {Ux,Uy} {Vx,Vy}
     double2* G1 = G0 + (ORDER == 2 ? Q.nl_max : 0);
     double2* G2 = G1 + (ORDER == 2 ? Q.nl_max : 0);
     double2* G3 = G2 + (ORDER == 2 ? Q.nl_max : 0);
-    double2* F0 = G3 + (ORDER == 2 ? Q.nl_max : 0);
+    double2* F0 = G3 + (ORDER == 2 ? Q.nl_max : 0);       // edge fluxes {fr,fu} {fv,fe} * l/2
     double2* F1 = F0 + Q.ne_max;
+    double* Es = reinterpret_cast<double*>(F1 + Q.ne_max); // LF only: total specific energy re/ro
     const int t = Q.tile_ids ? Q.tile_ids[blockIdx.x] : (int)blockIdx.x;
     const TileInfo ti = Q.tiles[t];
     const int tid = threadIdx.x;
 
+    // ---------------- phase 0: stage the primitive state of the tile + ring 1 -----------------
+    // one independent 32-byte load per thread and pass: this is where the memory parallelism is
+    for (int j = tid; j < ti.n_l; j += NT) {
+        const int c = j < ti.n_own ? ti.cbeg + j : __ldg(Q.ring + ti.roff + (j - ti.n_own));
+        double4 w = ld4(W, c);
+        W0[j] = make_double2(w.x, w.y);
+        W1[j] = make_double2(w.z, w.w);
+        if (FLUX == 1) { double4 u = ld4cg(Uin, c); Es[j] = u.w / u.x; }   // pL.E / pR.E of calcFlux's LF block
+    }
+    __syncthreads();
+
     // ---------------- phase 1: Green-Gauss gradients (k_grad arithmetic) ----------------------
     if (ORDER == 2) {
         for (int j = tid; j < ti.n_l; j += NT) {
-            const int c = j < ti.n_own ? ti.cbeg + j : __ldg(Q.ring + ti.roff + (j - ti.n_own));
             if (j < ti.n_g) {
-                double4 ws = ld4(W, c);
+                const int c = j < ti.n_own ? ti.cbeg + j : __ldg(Q.ring + ti.roff + (j - ti.n_own));
+                double2 wa = W0[j], wb = W1[j];
+                double4 ws = make_double4(wa.x, wa.y, wb.x, wb.y);
                 double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
                 for (int k = 0; k < 3; k++) {
@@ -65,7 +83,11 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
                     double nx = __ldg(Q.g_nx + o), ny = __ldg(Q.g_ny + o), l = __ldg(Q.g_l + o);
                     double4 wn;
                     if (nb >= 0) {
-                        wn = ld4(W, nb);
+                        const unsigned int ln = (unsigned int)(nb - ti.cbeg);
+                        if (ln < (unsigned int)ti.n_own) {           // neighbour inside the tile: staged copy
+                            double2 a = W0[ln], b = W1[ln];
+                            wn = make_double4(a.x, a.y, b.x, b.y);
+                        } else wn = ld4(W, nb);                      // ring 1 / ring 2: L2
                     } else {
                         int ib = -1 - nb;
                         MatC m = get_mat(P, c);
@@ -86,6 +108,7 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
                 G3[j] = make_double2(g[6] / si, g[7] / si);
             } else {
                 // rank-halo cell: the owner's gradient, received by the halo exchange
+                const int c = __ldg(Q.ring + ti.roff + (j - ti.n_own));
                 double4 ga = ld4cg(Gx, 2 * c), gb = ld4cg(Gx, 2 * c + 1);
                 G0[j] = make_double2(ga.x, ga.y);
                 G1[j] = make_double2(ga.z, ga.w);
@@ -97,6 +120,7 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
     }
 
     // ---------------- phase 2: reconstruction + numerical flux (k_flux arithmetic) ------------
+    // only coalesced streaming loads (the tile's edge tables); cell data come from shared memory
     {
         const int nwork = (2 * ti.ne_t + 31) & ~31;
         for (int w = tid; w < nwork; w += NT) {
@@ -105,19 +129,18 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
             const bool live = q < ti.ne_t;
             if (!live) q = ti.ne_t - 1;
             const size_t eo = (size_t)ti.eoff + q;
-            const int c1 = __ldg(Q.e_c1 + eo), c2 = __ldg(Q.e_c2 + eo);
             const unsigned int cl = __ldg(Q.e_cl + eo);
             const int l1 = (int)(cl & 0xffffu), l2 = (int)(cl >> 16);
+            const bool inner = l2 != 0xffff;
             double2 n = __ldg(Q.e_n + eo);
-            double4 w1 = ld4(W, c1);
-            Prim L = {w1.x, w1.y, w1.z, w1.w};
+            double2 wa = W0[l1], wb = W1[l1];
+            Prim L = {wa.x, wa.y, wb.x, wb.y};
             Prim R;
             double EL = 0.0, ER = 0.0;
-            if (FLUX == 1) { double4 u = ld4cg(Uin, c1); EL = u.w / u.x; }
-            const bool inner = c2 >= 0;
+            if (FLUX == 1) EL = Es[l1];
             double T1 = 0.0;
             MatC m;
-            if (!inner) { m = get_mat(P, c1); T1 = prim_T(L, m); }   // cell-centre T, before extrapolation
+            if (!inner) { m = get_mat(P, ti.cbeg + l1); T1 = prim_T(L, m); }   // a boundary edge's c1 is a tile cell
             if (ORDER == 2) {
                 double2 d = __ldg(reinterpret_cast<const double2*>(Q.e_d1 + eo) + gp);
                 double2 a = G0[l1], b = G1[l1], cc = G2[l1], dd = G3[l1];
@@ -127,9 +150,9 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
                 L.v += dd.x * d.x + dd.y * d.y;
             }
             if (inner) {
-                double4 w2 = ld4(W, c2);
-                R.r = w2.x; R.p = w2.y; R.u = w2.z; R.v = w2.w;
-                if (FLUX == 1) { double4 u = ld4cg(Uin, c2); ER = u.w / u.x; }
+                double2 va = W0[l2], vb = W1[l2];
+                R.r = va.x; R.p = va.y; R.u = vb.x; R.v = vb.y;
+                if (FLUX == 1) ER = Es[l2];
                 if (ORDER == 2) {
                     double2 d = __ldg(reinterpret_cast<const double2*>(Q.e_d2 + eo) + gp);
                     double2 a = G0[l2], b = G1[l2], cc = G2[l2], dd = G3[l2];
@@ -139,7 +162,7 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
                     R.v += dd.x * d.x + dd.y * d.y;
                 }
             } else {
-                int ib = -1 - c2;
+                int ib = -1 - __ldg(Q.e_c2 + eo);
                 R = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
             }
             double f0, f1, f2, f3;

@@ -138,7 +138,10 @@ __global__ void __launch_bounds__(256) k_tau_fill(KParams P, double tau) {
 // (the outward normal s*n reproduces the sign exactly) -- then the true division by S.  No atomics.
 // ---------------------------------------------------------------------------------------------
 // `list` (optional): only these n cells (multi-GPU: the cells whose gradients are sent to a peer).
-__global__ void __launch_bounds__(256) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G,
+#ifndef CFD2D_GRAD_MINB
+#define CFD2D_GRAD_MINB 4     // 64 registers: 0.182 -> 0.174 ms at 4 M cells (profiles/README.md)
+#endif
+__global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G,
                                               const int* __restrict__ list, int n) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
@@ -189,6 +192,7 @@ __global__ void __launch_bounds__(256) k_grad(KParams P, const double4* __restri
 #ifndef CFD2D_FLUX_MINB
 #define CFD2D_FLUX_MINB 8
 #endif
+
 template <int FLUX, int ORDER>
 __global__ void __launch_bounds__(128, FLUX == 0 ? CFD2D_FLUX_MINB : 8)
 k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,

@@ -54,7 +54,7 @@ struct TilePlan {
     std::vector<int> g_nb;                       // [goff + k*gstride + j] neighbour id or -1-bc
     std::vector<double> g_nx, g_ny, g_l;         // outward normal (sign*Edge::n), Edge::l
     std::vector<int> e_c1, e_c2;                 // global (device) cell ids; c2 = -1-bc on a boundary edge
-    std::vector<uint32_t> e_cl;                  // local ids: l1 | l2 << 16
+    std::vector<uint32_t> e_cl;                  // local ids: l1 | l2 << 16 (l2 = 0xffff on a boundary edge)
     std::vector<int> e_id;                       // caller's edge id (tests / debugging)
     std::vector<int> u_es;                       // [k*nc + c] local edge position*2 + (cell is c2)
     std::vector<int> interior, boundary;         // tile ids without / with rank-halo dependence
@@ -171,7 +171,7 @@ static inline std::string build_tile_plan(const HostMesh& m, int TC, TilePlan& p
         }
         ti.n_g = n_own + (int)ring_c.size();
         ti.n_l = ti.n_g + (int)ring_h.size();
-        if (ti.n_l > 65535) return "tile too large for 16-bit local cell ids";
+        if (ti.n_l > 65534) return "tile too large for 16-bit local cell ids";
         if (!ring_h.empty()) ti.halo_dep = 1;
         ti.roff = (int)p.ring.size();
         for (size_t i = 0; i < ring_c.size(); i++) { lidx[ring_c[i]] = n_own + (int)i; p.ring.push_back(ring_c[i]); }
@@ -210,8 +210,9 @@ static inline std::string build_tile_plan(const HostMesh& m, int TC, TilePlan& p
             const int c1 = m.edge_c1[e], c2 = m.edge_c2[e];
             const bool own1 = c1 >= cbeg && c1 < cbeg + n_own;
             const int l1 = own1 ? c1 - cbeg : lidx[c1];
-            int l2 = 0;
+            int l2 = 0xffff;                                  // boundary edge marker
             if (c2 >= 0) l2 = (c2 >= cbeg && c2 < cbeg + n_own) ? c2 - cbeg : lidx[c2];
+            if (c2 < 0 && !own1) return "internal: boundary edge whose cell is outside the tile";
             if (!own1 && cstamp[c1] != stamp) return "internal: edge cell outside tile + ring 1";
             p.e_c1.push_back(c1);
             p.e_c2.push_back(c2 >= 0 ? c2 : -1 - m.edge_bc[e]);

@@ -30,6 +30,7 @@ def main():
         flux, order = (int(x) for x in v.split(":"))
         for tc in a.tiles.split(","):
             for nt in a.nts.split(","):
+                os.environ["CFD2D_FUSED"] = "1"
                 os.environ["CFD2D_TILE"] = tc
                 os.environ["CFD2D_NT"] = nt
                 try:
