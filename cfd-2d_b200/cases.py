@@ -36,17 +36,23 @@ class Case:
             ro[sel], ru[sel], rv[sel], re[sel] = s
         return ro, ru, rv, re
 
-    def smooth_state(self, amp=0.05, u0=50.0, v0=0.0, T0=300.0, p0=1.0e5, sigma_frac=0.08):
+    def smooth_state(self, amp=0.05, u0=50.0, v0=0.0, T0=300.0, p0=1.0e5, sigma_frac=0.08, tiles=1):
         """Gaussian pressure bump on a uniform stream (the reference terminates on it).
-        Returned as conservative variables with the reference's own conversions."""
+        Returned as conservative variables with the reference's own conversions.
+        ``tiles`` > 1 (weak-scaling runs): the domain is ``tiles`` slabs side by side in x and every
+        slab carries the bump of the one-slab case, so each rank solves statistically the same
+        problem as the single-GPU run (the exact Riemann solver's cost depends on the data)."""
         m = self.task.materials[0]
         cx, cy = self.mesh.cell_cx, self.mesh.cell_cy
-        lx = self.nodes[:, 0].max() - self.nodes[:, 0].min()
+        x0 = self.nodes[:, 0].min()
+        lx = (self.nodes[:, 0].max() - x0) / tiles
         ly = self.nodes[:, 1].max() - self.nodes[:, 1].min()
-        xc = self.nodes[:, 0].min() + 0.4 * lx
         yc = self.nodes[:, 1].min() + 0.5 * ly
         sig = sigma_frac * max(lx, ly)
-        bump = np.exp(-((cx - xc) ** 2 + (cy - yc) ** 2) / (sig * sig))
+        bump = np.zeros_like(cx)
+        for k in range(tiles):
+            xc = x0 + (k + 0.4) * lx
+            bump += np.exp(-((cx - xc) ** 2 + (cy - yc) ** 2) / (sig * sig))
         p = p0 * (1.0 + amp * bump)
         T = np.full_like(p, T0)
         u = u0 * (1.0 + 0.1 * amp * bump)

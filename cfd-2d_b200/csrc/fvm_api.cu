@@ -34,6 +34,8 @@ struct cfd2d_fvm {
     size_t stage_smem = 0;
     int *d_interior = nullptr, *d_boundary = nullptr;
     bool overlap = true;          // multi-rank: halo exchange on the comm stream, overlapped with interior work
+    bool diag_split = false;      // diagnostics only (CFD2D_DIAG_SPLIT=1): serial handle runs the multi-rank kernel split
+    bool skip_exchange = false;   // diagnostics only (CFD2D_DIAG_NO_EXCHANGE=1): results are wrong, timing shows the cost of the exchanges
     int ne_int = 0;               // device edges [0, ne_int) touch owned cells only; [ne_int, ne) touch a halo cell
     int *d_cells_int = nullptr, *d_cells_bnd = nullptr;   // owned cells without / with a halo neighbour
     int n_cells_int = 0, n_cells_bnd = 0;
@@ -144,7 +146,7 @@ static void launch_prim(cfd2d_fvm* h, const double4* U, double4* W, int c0, int 
 
 // list == nullptr: all owned cells
 static void launch_grad(cfd2d_fvm* h, const int* list = nullptr, int n = -1, cudaStream_t st = nullptr) {
-    if (!list) n = h->nc;
+    if (!list && n < 0) n = h->nc;
     if (n <= 0) return;
     if (!st) st = h->stream;
     KTimer t(h, CFD2D_K_GRAD, st);
@@ -222,7 +224,7 @@ static void launch_stage(cfd2d_fvm* h, int stage, const int* tiles, int n) {
 static int exchange_U(cfd2d_fvm* h, double4* U, double4* W, cudaStream_t st) {
     if (!h->halo) return 0;
     KTimer t(h, CFD2D_K_HALO, st);
-    int rc = halo_exchange(h->halo, U, 1, st, &h->launches);
+    int rc = h->skip_exchange ? 0 : halo_exchange(h->halo, U, 1, st, &h->launches);
     if (rc) { h->error = halo_error(h->halo); return rc; }
     launch_prim(h, U, W, h->nc, h->nc_ex, st);
     return 0;
@@ -231,7 +233,7 @@ static int exchange_U(cfd2d_fvm* h, double4* U, double4* W, cudaStream_t st) {
 static int exchange_G(cfd2d_fvm* h, cudaStream_t st) {
     if (!h->halo || h->ctrl.order != 2) return 0;
     KTimer t(h, CFD2D_K_HALO, st);
-    int rc = halo_exchange(h->halo, h->G, 2, st, &h->launches);
+    int rc = h->skip_exchange ? 0 : halo_exchange(h->halo, h->G, 2, st, &h->launches);
     if (rc) h->error = halo_error(h->halo);
     return rc;
 }
@@ -255,7 +257,7 @@ static int enqueue_step_unfused(cfd2d_fvm* h) {
     if (h->ctrl.steady) launch_tau_steady(h);                 // :315
     for (int stage = 1; stage <= 2; stage++) {
         double4* Ucur = stage == 1 ? h->Ua : h->Ub;          // state this stage starts from
-        if (!multi) {
+        if (!multi && !h->diag_split) {
             if (o2) launch_grad(h);
             launch_flux(h, Ucur, 1);
         } else {
@@ -645,6 +647,15 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
                  nc ? (double)tp.sum_ring / nc : 0.0, nc ? (double)tp.sum_ne / nc : 0.0, h->stage_nt);
         h->plan_summary = b;
     }
+    if (!(halo && halo->nranks > 1)) {
+        if (const char* ev = getenv("CFD2D_DIAG_SPLIT")) h->diag_split = atoi(ev) != 0;
+        if (h->diag_split) {
+            std::vector<int> ci(nc);
+            for (int i = 0; i < nc; i++) ci[i] = i;
+            h->n_cells_int = nc; h->n_cells_bnd = 0;
+            { const int* q = nullptr; TRY(dev_upload(h, &q, ci)); h->d_cells_int = (int*)q; }
+        }
+    }
     if (halo && halo->nranks > 1) {
         std::string herr;
         // the send lists name the caller's cells: translate to device ids
@@ -681,6 +692,7 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         { const int* q = nullptr; TRY(dev_upload(h, &q, ci)); h->d_cells_int = (int*)q; }
         { const int* q = nullptr; TRY(dev_upload(h, &q, cb)); h->d_cells_bnd = (int*)q; }
         if (const char* ev = getenv("CFD2D_OVERLAP")) h->overlap = atoi(ev) != 0;
+        if (const char* ev = getenv("CFD2D_DIAG_NO_EXCHANGE")) h->skip_exchange = atoi(ev) != 0;
         {   // highest priority: the small pack / NCCL kernels must not queue behind a full-GPU sweep
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);

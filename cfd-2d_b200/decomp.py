@@ -214,7 +214,7 @@ def make_rank_solver(nx, ny, rank, world, device, flux, order, dist, partition="
     """Weak-scaling layout: a (world*nx) x ny x 2 channel, partitioned `world` ways."""
     from . import cases, fvm
     c = case if case is not None else cases.channel(nx * world, ny)
-    st = state if state is not None else c.smooth_state()
+    st = state if state is not None else c.smooth_state(tiles=world if case is None else 1)
     part = slab_part(c.mesh, world) if partition == "slab" else metis_part(c.mesh, world)
     rm = decompose(c.mesh, part, world, only_rank=rank)[rank]
     uid = nccl_unique_id(dist, rank)
