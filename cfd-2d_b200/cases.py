@@ -36,7 +36,7 @@ class Case:
             ro[sel], ru[sel], rv[sel], re[sel] = s
         return ro, ru, rv, re
 
-    def smooth_state(self, amp=0.05, u0=50.0, v0=0.0, T0=300.0, p0=1.0e5, sigma_frac=0.08, tiles=1):
+    def smooth_state(self, amp=0.05, u0=50.0, v0=0.0, T0=300.0, p0=1.0e5, sigma_frac=0.08, tiles=1, extent=None):
         """Gaussian pressure bump on a uniform stream (the reference terminates on it).
         Returned as conservative variables with the reference's own conversions.
         ``tiles`` > 1 (weak-scaling runs): the domain is ``tiles`` slabs side by side in x and every
@@ -44,10 +44,12 @@ class Case:
         problem as the single-GPU run (the exact Riemann solver's cost depends on the data)."""
         m = self.task.materials[0]
         cx, cy = self.mesh.cell_cx, self.mesh.cell_cy
-        x0 = self.nodes[:, 0].min()
-        lx = (self.nodes[:, 0].max() - x0) / tiles
-        ly = self.nodes[:, 1].max() - self.nodes[:, 1].min()
-        yc = self.nodes[:, 1].min() + 0.5 * ly
+        if extent is None:
+            extent = (self.nodes[:, 0].min(), self.nodes[:, 0].max(), self.nodes[:, 1].min(), self.nodes[:, 1].max())
+        x0 = extent[0]                     # extent of the WHOLE domain (this case may be a window of it)
+        lx = (extent[1] - x0) / tiles
+        ly = extent[3] - extent[2]
+        yc = extent[2] + 0.5 * ly
         sig = sigma_frac * max(lx, ly)
         bump = np.zeros_like(cx)
         for k in range(tiles):
@@ -122,10 +124,11 @@ def strip(nx=200, ny=50, jump="weak", jitter=0.0, shuffle=False, h=1.0) -> Case:
     return _finish(f"strip{nx}x{ny}", nodes, tris, {"left": left, "right": right}, {"walls": walls}, t)
 
 
-def channel(nx=200, ny=100, jitter=0.0, shuffle=False, h=1.0, two_materials=False) -> Case:
+def channel(nx=200, ny=100, jitter=0.0, shuffle=False, h=1.0, two_materials=False, x0=0.0) -> Case:
     """C2/C3/C5-style channel: inlet left, outlet right, slip wall bottom, no-slip wall top.
-    One region (uniform stream); smooth initial data are injected with ``Case.smooth_state``."""
-    nodes, tris, sides = _mesh.rect_tri_nodes(nx, ny, nx * h, ny * h, jitter)
+    One region (uniform stream); smooth initial data are injected with ``Case.smooth_state``.
+    ``x0``: x of the left side (a window of a longer channel, see decomp.slab_rank_mesh)."""
+    nodes, tris, sides = _mesh.rect_tri_nodes(nx, ny, nx * h, ny * h, jitter, x0=x0)
     if shuffle:
         tris = _mesh.shuffle_cells(tris)
     t = _task.Task(TAU=1.0e10)

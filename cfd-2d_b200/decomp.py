@@ -160,6 +160,32 @@ def _local_mesh(m: _mesh.Mesh, rm: RankMesh, l: np.ndarray) -> dict:
     return loc
 
 
+def slab_rank_mesh(nx: int, ny: int, rank: int, world: int, h: float = 1.0):
+    """The share of ``rank`` in the slab partition of the (world*nx) x ny channel, built WITHOUT the
+    global mesh: the rank's nx columns plus one column of quads on each interior side, decomposed
+    three ways (left pad | mine | right pad).  Cells, edges, halo order and send lists come out
+    exactly as ``decompose(channel(world*nx, ny), slab_part(..))`` gives them (the numberings of the
+    window and of the whole channel are order-isomorphic, and with h = 1 the coordinates are the same
+    doubles) -- tests/test_decomp.py::test_slab_window_equals_global_decomposition -- at O(nx*ny)
+    instead of O(world*nx*ny) time and memory per rank.  Returns (window case, RankMesh)."""
+    from . import cases
+    pad_l = 1 if rank > 0 else 0
+    pad_r = 1 if rank < world - 1 else 0
+    x_lo = rank * nx * h
+    c = cases.channel(nx + pad_l + pad_r, ny, h=h, x0=x_lo - pad_l * h)
+    cx = c.mesh.cell_cx
+    part = np.where(cx < x_lo, 0, np.where(cx < x_lo + nx * h, 1, 2)).astype(np.int32)
+    rm3 = decompose(c.mesh, part, 3, only_rank=1)[1]
+    recv = np.zeros(world, dtype=np.int32)
+    send = [np.empty(0, np.int32) for _ in range(world)]
+    if pad_l:
+        recv[rank - 1] = rm3.recv_count[0]; send[rank - 1] = rm3.send_ind[0]
+    if pad_r:
+        recv[rank + 1] = rm3.recv_count[2]; send[rank + 1] = rm3.send_ind[2]
+    rm = dataclasses.replace(rm3, rank=rank, nranks=world, recv_count=recv, send_ind=send)
+    return c, rm
+
+
 def parse_proc_file(path: str) -> dict:
     """Integer maps of a reference ``mesh.NNNN.proc`` file (format: decomp.cpp:295-334)."""
     with open(path) as f:
@@ -213,6 +239,15 @@ def nccl_unique_id(dist, rank: int) -> bytes:
 def make_rank_solver(nx, ny, rank, world, device, flux, order, dist, partition="slab", case=None, state=None):
     """Weak-scaling layout: a (world*nx) x ny x 2 channel, partitioned `world` ways."""
     from . import cases, fvm
+    if case is None and partition == "slab":
+        # weak-scaling bench: build only this rank's window of the channel
+        c, rm = slab_rank_mesh(nx, ny, rank, world)
+        st = c.smooth_state(tiles=world, extent=(0.0, float(world * nx), 0.0, float(ny)))
+        uid = nccl_unique_id(dist, rank)
+        s = fvm.Solver(rm.local, c.task, flux, order, device=device, nc_owned=rm.nc, halo=rm.halo_dict(uid))
+        own = rm.g_cells[:rm.nc]
+        s.rank_mesh = rm
+        return s, tuple(x[own] for x in st), rm.nc, 2 * nx * ny * world
     c = case if case is not None else cases.channel(nx * world, ny)
     st = state if state is not None else c.smooth_state(tiles=world if case is None else 1)
     part = slab_part(c.mesh, world) if partition == "slab" else metis_part(c.mesh, world)

@@ -174,3 +174,27 @@ def test_halo_exchange_logic_gloo_world2():
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res)
     assert all(t == 1.0 for _, _, t in res)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_window_equals_global_decomposition(world):
+    """decomp.slab_rank_mesh (the bench's O(cells per rank) path) == the slab decomposition of the
+    whole channel: local mesh arrays, halo layout, send lists and the initial state, bit for bit."""
+    from cfd2d_b200 import cases
+    nx, ny = 12, 6
+    g = cases.channel(nx * world, ny)
+    gst = g.smooth_state(tiles=world)
+    part = decomp.slab_part(g.mesh, world)
+    rms = decomp.decompose(g.mesh, part, world)
+    for r in range(world):
+        c, rm = decomp.slab_rank_mesh(nx, ny, r, world)
+        ref = rms[r]
+        assert (rm.nc, rm.nc_ex) == (ref.nc, ref.nc_ex)
+        assert np.array_equal(rm.recv_count, ref.recv_count)
+        for a, b in zip(rm.send_ind, ref.send_ind):
+            assert np.array_equal(a, b)
+        for k in ref.local:
+            assert np.array_equal(np.asarray(rm.local[k]), np.asarray(ref.local[k])), (r, k)
+        st = c.smooth_state(tiles=world, extent=(0.0, float(world * nx), 0.0, float(ny)))
+        for a, b in zip(st, gst):
+            assert np.array_equal(a[rm.g_cells[:rm.nc]], b[ref.g_cells[:ref.nc]])
