@@ -196,12 +196,40 @@ def run_reference_arm(a):
 
 
 def workload_config(a):
-    return {"workload": f"BASELINE configs[2]: synthetic {a.nx}x{a.ny}x2 = {2 * a.nx * a.ny} -cell triangulated channel per GPU, "
-                        f"inlet/outlet/walls, smooth IC; RK2; order {a.order}; flux {a.flux}",
-            "cells_per_gpu": 2 * a.nx * a.ny, "flux": a.flux, "order": a.order,
+    strong = getattr(a, "strong", False) and a.gpus > 1
+    per = 2 * a.nx * a.ny // (a.gpus if strong else 1)
+    return {"workload": (f"BASELINE configs[3]: synthetic {a.nx}x{a.ny}x2 = {2 * a.nx * a.ny}-cell triangulated channel split over {a.gpus} GPUs, "
+                         if strong else
+                         f"BASELINE configs[2]: synthetic {a.nx}x{a.ny}x2 = {2 * a.nx * a.ny} -cell triangulated channel per GPU, ")
+                        + f"inlet/outlet/walls, smooth IC; RK2; order {a.order}; flux {a.flux}",
+            "cells_per_gpu": per, "flux": a.flux, "order": a.order,
             "partition": (a.partition if a.gpus > 1 else "none"),
             "initial_state": "one Gaussian pressure bump per 4 M-cell slab (N slabs side by side: every rank solves the single-GPU problem)",
             "l2_policy": "inputs larger than L2 (working set ~1.9 GB at 4 M cells vs 126 MB L2)"}
+
+
+def bind_to_gpu_numa_node(local: int):
+    """Multi-rank runs: pin this process (and therefore its first-touch host allocations, the pinned
+    staging buffers of the e2e leg included) to the CPUs of the NUMA node its GPU hangs off, as an MPI
+    launcher's binding would.  Best effort; returns a short description for the JSON line."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        bus = out[-12:] if len(out) >= 12 else out          # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return "numa: single node"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node} ({len(cpus)} cpus)"
+    except Exception as ex:
+        return "numa: not bound (" + type(ex).__name__ + ")"
+    return "numa: not bound"
 
 
 # ------------------------------------------------------------------------------------------------
@@ -219,6 +247,9 @@ def main():
     ap.add_argument("--no-variants", action="store_true", help="skip the extra Lax-Friedrichs variant lines")
     ap.add_argument("--partition", default="slab", choices=["slab", "metis"],
                     help="N>1: slab (default; O(N) setup) or the bundled METIS as the reference's Decomp (decomp.cpp:104)")
+    ap.add_argument("--strong", action="store_true",
+                    help="N>1: strong scaling -- the (nx x ny x 2)-cell mesh is the WHOLE job, split N ways "
+                         "(BASELINE configs[3]: --nx 8000 --ny 2000 = 32 M cells); default is weak scaling (nx x ny x 2 per GPU)")
     ap.add_argument("--fused", action="store_true", help="one tile-fused kernel per stage (k_stage) instead of k_grad, k_flux, k_update")
     a = ap.parse_args()
     if a.impl == "reference":
@@ -234,6 +265,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else "numa: not bound (single rank)"
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -247,8 +279,15 @@ def main():
         nc_local, nc_total = c.mesh.nc, c.mesh.nc
     else:
         from cfd2d_b200 import decomp
-        s, st, nc_local, nc_total = decomp.make_rank_solver(a.nx, a.ny, rank, world, local, flux, a.order, dist,
-                                                            partition=a.partition)
+        nx_rank = a.nx
+        if a.strong:
+            if a.nx % world:
+                raise SystemExit("--strong needs nx divisible by the number of GPUs")
+            nx_rank = a.nx // world
+        # strong scaling: the global problem (mesh AND initial state) must not depend on N
+        s, st, nc_local, nc_total = decomp.make_rank_solver(nx_rank, a.ny, rank, world, local, flux, a.order, dist,
+                                                            partition=a.partition,
+                                                            tiles=max(1, a.nx // 1000) if a.strong else None)
     if a.fused:
         s.use_fused(True)
     stream = torch.cuda.Stream()          # a real (capturable) stream; torch events are recorded on it
@@ -371,11 +410,12 @@ def main():
     e2e = {"value": nc_total * 2.0 * e2e_steps / e2e_s, "unit": "cell-updates/s",
            "h2d_bytes_per_step": 32 * nc_local, "d2h_bytes_per_step": 32 * nc_local,
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
-           "what": "cfd2d_fvm_set_state(pinned host) + cfd2d_fvm_step(1) + cfd2d_fvm_get_state(pinned host) per step"}
+           "what": "cfd2d_fvm_set_state(pinned host) + cfd2d_fvm_step(1) + cfd2d_fvm_get_state(pinned host) per step",
+           "host_binding": numa}
 
     line = {"metric": "cell-updates/sec (FP64, RK stage)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if (a.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "setup_s": setup_s}
 

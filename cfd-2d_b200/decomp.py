@@ -236,20 +236,20 @@ def nccl_unique_id(dist, rank: int) -> bytes:
     return bytes(t.cpu().numpy().tobytes())
 
 
-def make_rank_solver(nx, ny, rank, world, device, flux, order, dist, partition="slab", case=None, state=None):
+def make_rank_solver(nx, ny, rank, world, device, flux, order, dist, partition="slab", case=None, state=None, tiles=None):
     """Weak-scaling layout: a (world*nx) x ny x 2 channel, partitioned `world` ways."""
     from . import cases, fvm
     if case is None and partition == "slab":
         # weak-scaling bench: build only this rank's window of the channel
         c, rm = slab_rank_mesh(nx, ny, rank, world)
-        st = c.smooth_state(tiles=world, extent=(0.0, float(world * nx), 0.0, float(ny)))
+        st = c.smooth_state(tiles=tiles or world, extent=(0.0, float(world * nx), 0.0, float(ny)))
         uid = nccl_unique_id(dist, rank)
         s = fvm.Solver(rm.local, c.task, flux, order, device=device, nc_owned=rm.nc, halo=rm.halo_dict(uid))
         own = rm.g_cells[:rm.nc]
         s.rank_mesh = rm
         return s, tuple(x[own] for x in st), rm.nc, 2 * nx * ny * world
     c = case if case is not None else cases.channel(nx * world, ny)
-    st = state if state is not None else c.smooth_state(tiles=world if case is None else 1)
+    st = state if state is not None else c.smooth_state(tiles=(tiles or world) if case is None else 1)
     part = slab_part(c.mesh, world) if partition == "slab" else metis_part(c.mesh, world)
     rm = decompose(c.mesh, part, world, only_rank=rank)[rank]
     uid = nccl_unique_id(dist, rank)
