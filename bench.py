@@ -52,7 +52,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.t_mark = [], None, index, 0.0
 
     def start(self):
         try:
@@ -66,7 +66,12 @@ class ClockSampler:
 
     def _read(self):
         for ln in self.proc.stdout:
-            self.rows.append(ln.strip())
+            self.rows.append((time.time(), ln.strip()))
+
+    def mark(self):
+        """Start of the timed region: the sampler itself is started earlier (nvidia-smi needs a few
+        hundred ms before its first line), only samples read after this mark are reported."""
+        self.t_mark = time.time()
 
     def stop(self):
         if not self.proc:
@@ -78,7 +83,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for ts, r in self.rows:
+            if ts < self.t_mark:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -303,12 +310,13 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident timing
-    s.step(a.warmup)
-    l0 = s.launch_count
     clocks = ClockSampler(local)
-    barrier()
     if rank == 0:
         clocks.start()
+    s.step(a.warmup)
+    l0 = s.launch_count
+    barrier()
+    clocks.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     s.step_async(a.steps)

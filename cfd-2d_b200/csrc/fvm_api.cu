@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,8 @@ struct cfd2d_fvm {
     cudaStream_t comm = nullptr;  // halo exchange stream (multi-rank handles)
     cudaEvent_t ev_G = nullptr, ev_stage = nullptr, ev_U = nullptr;
     std::vector<int> perm, orig;  // caller <-> device cell numbering
+    std::unique_ptr<HostMesh> pm; // renumbered host mesh (kept for the lazily built fused plan)
+    bool have_plan = false;
     std::string plan_summary;
     double* io[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // SoA staging for set/get
     unsigned long long* tau_bits = nullptr;
@@ -357,6 +360,79 @@ static int check_device_errors(cfd2d_fvm* h) {
     return 0;
 }
 
+// Host plan + device tables of the tile-fused stage kernel (fvm_tiling.h, fvm_fused.cuh); built on
+// first use from the renumbered mesh the handle keeps.
+static int build_fused_plan(cfd2d_fvm* h) {
+    if (h->have_plan) return 0;
+    if (!h->pm) { h->error = "internal: host mesh released"; return CFD2D_EINVAL; }
+    const HostMesh& pm = *h->pm;
+    const int nc = h->nc;
+    int rc = 0;
+#define FTRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    {
+        int TC = 512;
+        if (const char* ev = getenv("CFD2D_TILE")) TC = atoi(ev);
+        h->stage_nt = 512;
+        if (const char* ev = getenv("CFD2D_NT")) h->stage_nt = atoi(ev);
+        if (h->stage_nt != 128 && h->stage_nt != 256 && h->stage_nt != 384 && h->stage_nt != 512) h->stage_nt = 256;
+        TilePlan tp;
+        std::string terr = build_tile_plan(pm, TC, tp);
+        if (!terr.empty()) { h->error = terr; return CFD2D_EINVAL; }
+        h->ntiles = tp.ntiles;
+        h->n_interior = (int)tp.interior.size();
+        h->n_boundary = (int)tp.boundary.size();
+        const size_t net = tp.e_c1.size();
+        std::vector<double2> t_n(net);
+        std::vector<double> t_l2(net);
+        std::vector<double4> t_d1(net), t_d2(net);
+        for (size_t q = 0; q < net; q++) {
+            const int e = tp.e_id[q];
+            const int c1 = pm.edge_c1[e], c2 = pm.edge_c2[e];
+            t_n[q] = make_double2(pm.edge_nx[e], pm.edge_ny[e]);
+            t_l2[q] = pm.edge_l[e] * 0.5;                               // fvm_tvd.cpp:335
+            const double* g = pm.edge_gp.data() + 4 * (size_t)e;
+            t_d1[q] = make_double4(g[0] - pm.cell_cx[c1], g[1] - pm.cell_cy[c1], g[2] - pm.cell_cx[c1], g[3] - pm.cell_cy[c1]);
+            if (c2 >= 0) t_d2[q] = make_double4(g[0] - pm.cell_cx[c2], g[1] - pm.cell_cy[c2], g[2] - pm.cell_cx[c2], g[3] - pm.cell_cy[c2]);
+            else t_d2[q] = make_double4(0, 0, 0, 0);
+        }
+        FParams& Q = h->Q;
+        Q.tile_ids = nullptr;
+        Q.nl_max = tp.nl_max; Q.ne_max = tp.ne_max;
+        FTRY(dev_upload(h, &Q.tiles, tp.tiles));
+        FTRY(dev_upload(h, &Q.ring, tp.ring));
+        FTRY(dev_upload(h, &Q.g_nb, tp.g_nb));
+        FTRY(dev_upload(h, &Q.g_nx, tp.g_nx));
+        FTRY(dev_upload(h, &Q.g_ny, tp.g_ny));
+        FTRY(dev_upload(h, &Q.g_l, tp.g_l));
+        FTRY(dev_upload(h, &Q.e_c1, tp.e_c1));
+        FTRY(dev_upload(h, &Q.e_c2, tp.e_c2));
+        FTRY(dev_upload(h, &Q.e_cl, tp.e_cl));
+        FTRY(dev_upload(h, &Q.e_n, t_n));
+        FTRY(dev_upload(h, &Q.e_l2, t_l2));
+        FTRY(dev_upload(h, &Q.e_d1, t_d1));
+        FTRY(dev_upload(h, &Q.e_d2, t_d2));
+        FTRY(dev_upload(h, &Q.u_es, tp.u_es));
+        Q.c_orig = h->P.c_orig;
+        { const int* q = nullptr; FTRY(dev_upload(h, &q, tp.interior)); h->d_interior = (int*)q; }
+        { const int* q = nullptr; FTRY(dev_upload(h, &q, tp.boundary)); h->d_boundary = (int*)q; }
+        h->stage_smem = ((h->ctrl.order == 2 ? 6 * (size_t)tp.nl_max : 2 * (size_t)tp.nl_max) + 2 * (size_t)tp.ne_max) * sizeof(double2)
+                        + (h->ctrl.flux == CFD2D_FLUX_LAX ? (size_t)tp.nl_max * sizeof(double) : 0);
+        if (h->stage_smem > 227 * 1024) { h->error = "tile does not fit in shared memory (lower CFD2D_TILE)"; return CFD2D_EINVAL; }
+        for (int st = 1; st <= 2; st++) {
+            stage_fn f = stage_kernel(h, st);
+            CUDA_TRY(h, cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stage_smem));
+        }
+        char b[256];
+        snprintf(b, sizeof b, "tiles=%d (TC=%d, interior=%d, boundary=%d) nl_max=%d ne_max=%d smem=%zu B ring/own=%.3f edges/own=%.3f nt=%d",
+                 tp.ntiles, tp.TC, h->n_interior, h->n_boundary, tp.nl_max, tp.ne_max, h->stage_smem,
+                 nc ? (double)tp.sum_ring / nc : 0.0, nc ? (double)tp.sum_ne / nc : 0.0, h->stage_nt);
+        h->plan_summary = b;
+    }
+#undef FTRY
+    h->have_plan = true;
+    return 0;
+}
+
 extern "C" {
 
 const char* cfd2d_version(void) { return "cfd2d_b200 0.1 (sm_100a)"; }
@@ -581,72 +657,16 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     cudaMemset(h->G, 0, 2 * (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
     cudaMemset(P.cfl, 0, (size_t)(nc ? nc : 1) * sizeof(double));
     cudaMemset(P.ctau, 0, (size_t)(nc ? nc : 1) * sizeof(double));
-    // ---- tile plan of the fused stage kernel
-    // Default layout: three sweeps per stage.  Measured on B200 at 4 M cells (profiles/README.md) the
-    // fused kernel moves ~35 % fewer HBM bytes but its barrier-separated phases expose more load
-    // latency than the three full-width sweeps hide; it stays selectable (cfd2d_fvm_use_fused,
-    // CFD2D_FUSED=1) and is held to bit-identity with the sweeps by the tests.
+    // ---- step layout.  Default: three sweeps per stage.  Measured on B200 at 4 M cells
+    // (profiles/README.md) the tile-fused kernel moves ~35 % fewer HBM bytes but its barrier-separated
+    // phases expose more load latency than the three full-width sweeps hide; it stays selectable
+    // (cfd2d_fvm_use_fused, CFD2D_FUSED=1) and is held to bit-identity with the sweeps by the tests.
+    // Its plan (1-2 GB of tables at 4 M cells) is only built when it is selected.
     h->fused = false;
     if (const char* ev = getenv("CFD2D_FUSED")) h->fused = atoi(ev) != 0;
-    {
-        int TC = 512;
-        if (const char* ev = getenv("CFD2D_TILE")) TC = atoi(ev);
-        h->stage_nt = 512;
-        if (const char* ev = getenv("CFD2D_NT")) h->stage_nt = atoi(ev);
-        if (h->stage_nt != 128 && h->stage_nt != 256 && h->stage_nt != 384 && h->stage_nt != 512) h->stage_nt = 256;
-        TilePlan tp;
-        std::string terr = build_tile_plan(pm, TC, tp);
-        if (!terr.empty()) { g_create_error = terr; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
-        h->ntiles = tp.ntiles;
-        h->n_interior = (int)tp.interior.size();
-        h->n_boundary = (int)tp.boundary.size();
-        const size_t net = tp.e_c1.size();
-        std::vector<double2> t_n(net);
-        std::vector<double> t_l2(net);
-        std::vector<double4> t_d1(net), t_d2(net);
-        for (size_t q = 0; q < net; q++) {
-            const int e = tp.e_id[q];
-            const int c1 = pm.edge_c1[e], c2 = pm.edge_c2[e];
-            t_n[q] = make_double2(pm.edge_nx[e], pm.edge_ny[e]);
-            t_l2[q] = pm.edge_l[e] * 0.5;                               // fvm_tvd.cpp:335
-            const double* g = pm.edge_gp.data() + 4 * (size_t)e;
-            t_d1[q] = make_double4(g[0] - pm.cell_cx[c1], g[1] - pm.cell_cy[c1], g[2] - pm.cell_cx[c1], g[3] - pm.cell_cy[c1]);
-            if (c2 >= 0) t_d2[q] = make_double4(g[0] - pm.cell_cx[c2], g[1] - pm.cell_cy[c2], g[2] - pm.cell_cx[c2], g[3] - pm.cell_cy[c2]);
-            else t_d2[q] = make_double4(0, 0, 0, 0);
-        }
-        FParams& Q = h->Q;
-        Q.tile_ids = nullptr;
-        Q.nl_max = tp.nl_max; Q.ne_max = tp.ne_max;
-        TRY(dev_upload(h, &Q.tiles, tp.tiles));
-        TRY(dev_upload(h, &Q.ring, tp.ring));
-        TRY(dev_upload(h, &Q.g_nb, tp.g_nb));
-        TRY(dev_upload(h, &Q.g_nx, tp.g_nx));
-        TRY(dev_upload(h, &Q.g_ny, tp.g_ny));
-        TRY(dev_upload(h, &Q.g_l, tp.g_l));
-        TRY(dev_upload(h, &Q.e_c1, tp.e_c1));
-        TRY(dev_upload(h, &Q.e_c2, tp.e_c2));
-        TRY(dev_upload(h, &Q.e_cl, tp.e_cl));
-        TRY(dev_upload(h, &Q.e_n, t_n));
-        TRY(dev_upload(h, &Q.e_l2, t_l2));
-        TRY(dev_upload(h, &Q.e_d1, t_d1));
-        TRY(dev_upload(h, &Q.e_d2, t_d2));
-        TRY(dev_upload(h, &Q.u_es, tp.u_es));
-        Q.c_orig = P.c_orig;
-        { const int* q = nullptr; TRY(dev_upload(h, &q, tp.interior)); h->d_interior = (int*)q; }
-        { const int* q = nullptr; TRY(dev_upload(h, &q, tp.boundary)); h->d_boundary = (int*)q; }
-        h->stage_smem = ((c->order == 2 ? 6 * (size_t)tp.nl_max : 2 * (size_t)tp.nl_max) + 2 * (size_t)tp.ne_max) * sizeof(double2)
-                        + (c->flux == CFD2D_FLUX_LAX ? (size_t)tp.nl_max * sizeof(double) : 0);
-        if (h->stage_smem > 227 * 1024) { g_create_error = "tile does not fit in shared memory (lower CFD2D_TILE)"; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
-        for (int st = 1; st <= 2; st++) {
-            stage_fn f = stage_kernel(h, st);
-            CUDA_TRY(h, cudaFuncSetAttribute((const void*)f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stage_smem));
-        }
-        char b[256];
-        snprintf(b, sizeof b, "tiles=%d (TC=%d, interior=%d, boundary=%d) nl_max=%d ne_max=%d smem=%zu B ring/own=%.3f edges/own=%.3f nt=%d",
-                 tp.ntiles, tp.TC, h->n_interior, h->n_boundary, tp.nl_max, tp.ne_max, h->stage_smem,
-                 nc ? (double)tp.sum_ring / nc : 0.0, nc ? (double)tp.sum_ne / nc : 0.0, h->stage_nt);
-        h->plan_summary = b;
-    }
+    h->pm.reset(new HostMesh(std::move(pm)));
+    const HostMesh& pmr = *h->pm;
+    if (h->fused) TRY(build_fused_plan(h));
     if (!(halo && halo->nranks > 1)) {
         if (const char* ev = getenv("CFD2D_DIAG_SPLIT")) h->diag_split = atoi(ev) != 0;
         if (h->diag_split) {
@@ -682,8 +702,8 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         for (int cc = 0; cc < nc; cc++) {
             bool b = false;
             for (int k = 0; k < 3; k++) {
-                int e = pm.cell_edges[3 * (size_t)cc + k];
-                int nb = pm.edge_c1[e] == cc ? pm.edge_c2[e] : pm.edge_c1[e];
+                int e = pmr.cell_edges[3 * (size_t)cc + k];
+                int nb = pmr.edge_c1[e] == cc ? pmr.edge_c2[e] : pmr.edge_c1[e];
                 if (nb >= nc) b = true;
             }
             (b ? cb : ci).push_back(cc);
@@ -749,6 +769,7 @@ int cfd2d_fvm_use_fused(cfd2d_fvm* h, int on) {
     cudaStreamSynchronize(h->stream);
     if (h->comm) cudaStreamSynchronize(h->comm);
     drop_graph(h);
+    if (on) { int rc = build_fused_plan(h); if (rc) return rc; }
     h->fused = on != 0;
     return 0;
 }
