@@ -7,7 +7,8 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -fmad=false -Xcompiler -fPIC,-O2,-ffp-contract=off ${CFD2D_NVCC_EXTRA}"
 $NVCC $FLAGS -Xptxas -v -c fvm_api.cu -o fvm_api.o 2> ptxas_fvm_api.log || { cat ptxas_fvm_api.log; exit 1; }
 $NVCC $FLAGS -c halo_nccl.cu -o halo_nccl.o
+${CXX:-g++} -O2 -std=c++17 -fPIC -c unv_reader.cpp -o unv_reader.o
 OUT=${CFD2D_OUT:-libcfd2d_b200.so}
-$NVCC -shared -o $OUT fvm_api.o halo_nccl.o -lcudart -ldl
+$NVCC -shared -o $OUT fvm_api.o halo_nccl.o unv_reader.o -lcudart -ldl
 grep -E "Compiling entry|registers|spill" ptxas_fvm_api.log | paste - - - | sed -E 's/ptxas info\s+: //g' | awk '{print}' > ptxas_summary.txt || true
 echo "built $(pwd)/$OUT"

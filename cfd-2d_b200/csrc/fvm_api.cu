@@ -15,6 +15,7 @@
 #include <vector>
 
 static thread_local std::string g_create_error;
+void cfd2d_set_create_error(const std::string& s) { g_create_error = s; }   // host-only helpers (unv_reader.cpp)
 
 struct cfd2d_fvm {
     int device = 0;

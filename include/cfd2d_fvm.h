@@ -205,6 +205,22 @@ int cfd2d_tiling_plan(const cfd2d_mesh* mesh, int tile_cells, int hilbert, int32
  * rank passes it in cfd2d_halo.nccl_unique_id.                                                    */
 int cfd2d_nccl_get_unique_id(void* out128);
 
+/* ---- mesh ingest (host only) -------------------------------------------------
+ * One linear pass over the Salome-UNV subset the reference reads (MeshReaderSalomeUnv.cpp:267-448:
+ * blocks 2411 nodes, 2412 fe_id 11 boundary edges / 41 triangles -- any other fe_id is the
+ * reference's "Unknown element type" error --, 2467 named groups), without its by-value string
+ * lists and linear searches (:14-22, :428).  Labels are returned 0-based like the reference stores
+ * them; groups are sorted by name (the reference's std::map order) and split into the cells and
+ * the boundary-edge node pairs they name.  Errors: CFD2D_EINVAL + cfd2d_fvm_last_error(NULL).      */
+typedef struct cfd2d_unv cfd2d_unv;
+int  cfd2d_unv_read(const char* path, cfd2d_unv** out);
+void cfd2d_unv_counts(const cfd2d_unv* u, int64_t* n_nodes, int64_t* n_cells, int64_t* n_bnd_edges, int32_t* n_groups);
+void cfd2d_unv_copy(const cfd2d_unv* u, double* xy /*[n_nodes][2]*/, int32_t* tris /*[n_cells][3]*/, int32_t* bnd_edges /*[n_bnd_edges][2]*/);
+const char* cfd2d_unv_group_name(const cfd2d_unv* u, int g);
+void cfd2d_unv_group_counts(const cfd2d_unv* u, int g, int64_t* n_cells, int64_t* n_edges);
+void cfd2d_unv_group_copy(const cfd2d_unv* u, int g, int64_t* cells, int32_t* edge_nodes /*[n_edges][2]*/);
+void cfd2d_unv_free(cfd2d_unv* u);
+
 const char* cfd2d_fvm_last_error(const cfd2d_fvm* h);   /* h == NULL -> last create() error         */
 const char* cfd2d_version(void);
 
