@@ -154,6 +154,8 @@ EXPORTS = [
     "cfd2d_fvm_time", "cfd2d_fvm_calc_grad", "cfd2d_fvm_edge_fluxes", "cfd2d_kat_rim_orig", "cfd2d_kat_calc_flux",
     "cfd2d_fvm_profile", "cfd2d_fvm_launch_count", "cfd2d_fvm_set_stream", "cfd2d_fvm_use_graph",
     "cfd2d_fvm_use_fused", "cfd2d_fvm_plan_summary", "cfd2d_tiling_plan",
+    "cfd2d_unv_read", "cfd2d_unv_counts", "cfd2d_unv_copy", "cfd2d_unv_group_name", "cfd2d_unv_group_counts",
+    "cfd2d_unv_group_copy", "cfd2d_unv_free",
     "cfd2d_fvm_last_error", "cfd2d_version",
 ]
 

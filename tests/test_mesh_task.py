@@ -88,3 +88,49 @@ def test_build_mesh_matches_live_reference_reader():
     st = s.state()
     for a, b in zip(c.initial_state(), st[:4]):
         assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# native UNV reader (csrc/unv_reader.cpp) == the Python parser, which the tests
+# above hold equal to the reference's MeshReaderSalomeUnv
+# ------------------------------------------------------------------------------------------------
+def _same_unv(a, b):
+    assert np.array_equal(a[0], b[0]) and a[0].dtype == b[0].dtype            # node coordinates: same doubles
+    assert np.array_equal(a[1], b[1])
+    assert list(a[2]) == list(b[2]) and list(a[3]) == list(b[3])             # group names, in std::map order
+    for k in a[2]:
+        assert np.array_equal(a[2][k], b[2][k])
+    for k in a[3]:
+        assert np.array_equal(a[3][k], b[3][k])
+
+
+@pytest.mark.parametrize("make", [
+    lambda: cases.strip(12, 5, jitter=0.2, shuffle=True),
+    lambda: cases.channel(9, 7, jitter=0.3, two_materials=True),          # odd group sizes -> the 4-int tail line
+    lambda: cases.forward_step(30, 10, jitter=0.15),
+])
+def test_native_unv_reader_equals_python_parser(make, tmp_path):
+    from cfd2d_b200 import unv
+    c = make()
+    c.write(str(tmp_path))
+    p = os.path.join(str(tmp_path), c.task.mesh_name)
+    _same_unv(unv.read_unv(p, native=True), unv.read_unv(p, native=False))
+    # the file as the generator writes it ends WITHOUT a newline; with one, and with CRLF, too
+    txt = open(p).read()
+    open(p, "w").write(txt + "\n")
+    _same_unv(unv.read_unv(p, native=True), unv.read_unv(p, native=False))
+
+
+def test_native_unv_reader_errors(tmp_path):
+    from cfd2d_b200 import unv
+    with pytest.raises(ValueError):
+        unv.read_unv(os.path.join(str(tmp_path), "missing.unv"), native=True)
+    c = cases.strip(4, 2)
+    c.write(str(tmp_path))
+    p = os.path.join(str(tmp_path), c.task.mesh_name)
+    txt = open(p).read().replace("        41         2", "        44         2", 1)   # a quad element
+    open(p, "w").write(txt)
+    with pytest.raises(ValueError, match="Unknown element type '44'"):
+        unv.read_unv(p, native=True)
+    with pytest.raises(ValueError, match="Unknown element type '44'"):
+        unv.read_unv(p, native=False)
