@@ -36,6 +36,7 @@ struct cfd2d_fvm {
     size_t stage_smem = 0;
     int *d_interior = nullptr, *d_boundary = nullptr;
     bool overlap = true;          // multi-rank: halo exchange on the comm stream, overlapped with interior work
+    bool lf1_cell = false;        // first-order Lax-Friedrichs on a serial handle: one cell-parallel sweep per stage (k_cell_lf1)
     bool diag_split = false;      // diagnostics only (CFD2D_DIAG_SPLIT=1): serial handle runs the multi-rank kernel split
     bool skip_exchange = false;   // diagnostics only (CFD2D_DIAG_NO_EXCHANGE=1): results are wrong, timing shows the cost of the exchanges
     int ne_int = 0;               // device edges [0, ne_int) touch owned cells only; [ne_int, ne) touch a halo cell
@@ -259,6 +260,15 @@ static int enqueue_step_unfused(cfd2d_fvm* h) {
     cudaStream_t S = h->stream, C = ov ? h->comm : h->stream;
     const bool o2 = h->ctrl.order == 2;
     if (h->ctrl.steady) launch_tau_steady(h);                 // :315
+    if (h->lf1_cell && !multi) {
+        // first-order LF: no gradients, fluxes evaluated from both sides => the stage is ONE sweep
+        if (h->nc > 0) {
+            { KTimer t(h, CFD2D_K_STAGE1); k_cell_lf1<1><<<nblk(h->nc, 256), 256, 0, S>>>(h->P, h->W, h->Ua, h->Ub, h->Wb); }
+            { KTimer t(h, CFD2D_K_STAGE2); k_cell_lf1<2><<<nblk(h->nc, 256), 256, 0, S>>>(h->P, h->Wb, h->Ub, h->Ua, h->W); }
+        }
+        launch_remediate(h);
+        return 0;
+    }
     for (int stage = 1; stage <= 2; stage++) {
         double4* Ucur = stage == 1 ? h->Ua : h->Ub;          // state this stage starts from
         if (!multi && !h->diag_split) {
@@ -669,6 +679,8 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     const HostMesh& pmr = *h->pm;
     if (h->fused) TRY(build_fused_plan(h));
     if (!(halo && halo->nranks > 1)) {
+        h->lf1_cell = (c->flux == CFD2D_FLUX_LAX && c->order == 1);
+        if (const char* ev = getenv("CFD2D_LF1_CELL")) h->lf1_cell = h->lf1_cell && atoi(ev) != 0;
         if (const char* ev = getenv("CFD2D_DIAG_SPLIT")) h->diag_split = atoi(ev) != 0;
         if (h->diag_split) {
             std::vector<int> ci(nc);

@@ -315,6 +315,87 @@ __global__ void __launch_bounds__(256) k_update(KParams P, const double4* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
+// K4c / K5c: the WHOLE RK stage of the first-order Lax-Friedrichs scheme (BASELINE configs[0]) in one
+// cell-parallel sweep.  Without reconstruction there is no gradient pass, and the LF flux is cheap
+// enough (2 sqrt, a few divisions) to be evaluated from BOTH sides of an edge, so the staged edge
+// fluxes (32 B written + 64 B gathered per edge) disappear as well: a cell reads its own and its
+// three neighbours' records and writes its new state -- ~220 B/cell/stage instead of ~400.
+// Bit-exactness: an edge's flux is formed by flux_lax_dev with the edge's own orientation
+// (L = c1, R = c2, Edge::n) whichever cell evaluates it, so both cells get the same bits as k_flux;
+// the two Gauss points of an edge see identical states, so the reference's (0.0 + f) + f is f + f;
+// the residual is accumulated in Cell::edgesInd order from 0.0 and updated exactly as in k_update.
+// W is ping-ponged (neighbours still read the old primitive state).
+// ---------------------------------------------------------------------------------------------
+#ifndef CFD2D_LF1_MINB
+#define CFD2D_LF1_MINB 4     // 64 registers, 32 warps per SM: 0.369 -> 0.248 ms per stage at 4 M cells
+#endif
+template <int STAGE>
+__global__ void __launch_bounds__(256, CFD2D_LF1_MINB) k_cell_lf1(KParams P, const double4* __restrict__ W, const double4* Uin, double4* Uout,
+                                                  double4* __restrict__ Wout) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nc) return;
+    unsigned int fl = P.flag[c];
+    if (fl & 2u) {                       // cellIsLim: frozen until remediated (:368, :421, :432)
+        st4(Wout, c, ld4(W, c));
+        if (STAGE == 1) st4(Uout, c, ld4cg(Uin, c));
+        else {
+            int pos = atomicAdd(P.err + 1, 1);
+            if (pos < P.lim_cap) P.lim_list[pos] = __ldg(P.c_orig + c);
+        }
+        return;
+    }
+    const double4 wc = ld4(W, c);
+    double4 u = ld4cg(Uin, c);
+    const Prim own = {wc.x, wc.y, wc.z, wc.w};
+    const double Eown = u.w / u.x;
+    MatC m = get_mat(P, c);
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const size_t o = (size_t)k * P.nc + c;
+        const int nb = __ldg(P.s_nb + o);
+        const double onx = __ldg(P.s_nx + o), ony = __ldg(P.s_ny + o);   // outward normal = +-Edge::n
+        const double l2 = __ldg(P.s_l + o) * 0.5;                        // fvm_tvd.cpp:335
+        const bool is_c2 = (__ldg(P.s_es + o) & 1) != 0;
+        double f0, f1, f2, f3;
+        if (nb >= 0) {
+            const double4 wn = ld4(W, nb);
+            const double4 un = ld4cg(Uin, nb);
+            const Prim oth = {wn.x, wn.y, wn.z, wn.w};
+            const double Eoth = un.w / un.x;
+            if (is_c2) flux_lax_dev(P.rim.GAM, oth, Eoth, own, Eown, -onx, -ony, f0, f1, f2, f3);
+            else       flux_lax_dev(P.rim.GAM, own, Eown, oth, Eoth, onx, ony, f0, f1, f2, f3);
+        } else {
+            const int ib = -1 - nb;
+            double ER = 0.0;
+            Prim R = ghost_state(own, prim_T(own, m), P.bc_kind[ib], P.bc_par + 4 * ib, onx, ony, m, &ER);
+            flux_lax_dev(P.rim.GAM, own, Eown, R, ER, onx, ony, f0, f1, f2, f3);
+        }
+        f0 = (f0 + f0) * l2; f1 = (f1 + f1) * l2; f2 = (f2 + f2) * l2; f3 = (f3 + f3) * l2;   // two Gauss points, then * l/2
+        if (is_c2) { r0 += f0; r1 += f1; r2 += f2; r3 += f3; }
+        else       { r0 -= f0; r1 -= f1; r2 -= f2; r3 -= f3; }
+    }
+    double cfl = P.cfl[c];
+    u.x += cfl * r0; u.y += cfl * r1; u.z += cfl * r2; u.w += cfl * r3;
+    if (STAGE == 2) {
+        double4 uo = ld4cg(Uout, c);     // Ua: the state at step start (ro_old ...)
+        u.x = 0.5 * (uo.x + u.x); u.y = 0.5 * (uo.y + u.y); u.z = 0.5 * (uo.z + u.z); u.w = 0.5 * (uo.w + u.w);
+    }
+    Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
+    st4(Uout, c, u);
+    st4(Wout, c, make_double4(w.r, w.p, w.u, w.v));
+    if (STAGE == 2) {
+        bool lim = (w.r < P.lim[0]) | (w.r > P.lim[1]) | (w.p < P.lim[2]) | (w.p > P.lim[3]) |
+                   (fabs(w.u) > P.lim[4]) | (fabs(w.v) > P.lim[4]);
+        if (lim) {
+            P.flag[c] = fl | 2u;         // setCellFlagLim
+            int pos = atomicAdd(P.err + 1, 1);
+            if (pos < P.lim_cap) P.lim_list[pos] = __ldg(P.c_orig + c);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6: FVM_TVD::remediateLimCells (fvm_tvd.cpp:464-499).  Rare path.  One block: sort the flagged
 // list ascending by caller id (bitonic, in global memory), then thread 0 replays the reference's in-place,
 // ascending-cell-order sweep (the order matters when two flagged cells are neighbours).  Keeps the
