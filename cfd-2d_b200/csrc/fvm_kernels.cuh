@@ -194,7 +194,10 @@ __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const 
 #endif
 
 template <int FLUX, int ORDER>
-__global__ void __launch_bounds__(128, FLUX == 0 ? CFD2D_FLUX_MINB : 8)
+#ifndef CFD2D_FLUXLF_MINB
+#define CFD2D_FLUXLF_MINB 8
+#endif
+__global__ void __launch_bounds__(128, FLUX == 0 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
 k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
        const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2, int e0, int e1) {
     // edges [e0, e1) of the device edge order (multi-rank handles: interior edges first, edges that

@@ -169,8 +169,9 @@ int cfd2d_kat_calc_flux(int device, int n, const double* in12, double gam, int f
 #define CFD2D_K_REMEDIATE 4   /* K6: remediateLimCells                                              */
 #define CFD2D_K_TIMESTEP  5   /* K1: steady local time step                                         */
 #define CFD2D_K_HALO      6   /* K7: halo pack + exchange                                           */
-#define CFD2D_K_STAGE1    7   /* K9: tile-fused RK stage 1 (gradients + fluxes + residual + update)  */
-#define CFD2D_K_STAGE2    8   /* K9: tile-fused RK stage 2 (+ half-sum + limit flags)                */
+#define CFD2D_K_STAGE1    7   /* whole RK stage 1 in one kernel: tile-fused k_stage (use_fused) or the  */
+                              /* single-sweep first-order Lax-Friedrichs kernel k_cell_lf1            */
+#define CFD2D_K_STAGE2    8   /* same for stage 2 (+ half-sum + limit flags)                          */
 #define CFD2D_NKERNELS    9
 int cfd2d_fvm_profile(cfd2d_fvm* h, int nsteps, double* ms, int64_t* launches);
 
