@@ -36,7 +36,7 @@ struct cfd2d_fvm {
     size_t stage_smem = 0;
     int *d_interior = nullptr, *d_boundary = nullptr;
     bool overlap = true;          // multi-rank: halo exchange on the comm stream, overlapped with interior work
-    bool lf1_cell = false;        // first-order Lax-Friedrichs on a serial handle: one cell-parallel sweep per stage (k_cell_lf1)
+    bool lf1_cell = false;        // first-order Lax-Friedrichs: one cell-parallel sweep per stage (k_cell_lf1)
     bool diag_split = false;      // diagnostics only (CFD2D_DIAG_SPLIT=1): serial handle runs the multi-rank kernel split
     bool skip_exchange = false;   // diagnostics only (CFD2D_DIAG_NO_EXCHANGE=1): results are wrong, timing shows the cost of the exchanges
     int ne_int = 0;               // device edges [0, ne_int) touch owned cells only; [ne_int, ne) touch a halo cell
@@ -260,11 +260,34 @@ static int enqueue_step_unfused(cfd2d_fvm* h) {
     cudaStream_t S = h->stream, C = ov ? h->comm : h->stream;
     const bool o2 = h->ctrl.order == 2;
     if (h->ctrl.steady) launch_tau_steady(h);                 // :315
-    if (h->lf1_cell && !multi) {
-        // first-order LF: no gradients, fluxes evaluated from both sides => the stage is ONE sweep
-        if (h->nc > 0) {
-            { KTimer t(h, CFD2D_K_STAGE1); k_cell_lf1<1><<<nblk(h->nc, 256), 256, 0, S>>>(h->P, h->W, h->Ua, h->Ub, h->Wb); }
-            { KTimer t(h, CFD2D_K_STAGE2); k_cell_lf1<2><<<nblk(h->nc, 256), 256, 0, S>>>(h->P, h->Wb, h->Ub, h->Ua, h->W); }
+    if (h->lf1_cell) {
+        // first-order LF: no gradients, fluxes evaluated from both sides => the stage is ONE sweep.
+        // Multi-rank: the cells with a halo neighbour run on the comm stream after the state exchange,
+        // all others on the compute stream meanwhile.  W ping-pongs: stage 1 W -> Wb, stage 2 Wb -> W.
+        for (int stage = 1; stage <= 2; stage++) {
+            const double4* Wc = stage == 1 ? h->W : h->Wb;
+            double4* Wo = stage == 1 ? h->Wb : h->W;
+            double4* Ui = stage == 1 ? h->Ua : h->Ub;
+            double4* Uo = stage == 1 ? h->Ub : h->Ua;
+            const int kid = stage == 1 ? CFD2D_K_STAGE1 : CFD2D_K_STAGE2;
+            auto sweep = [&](const int* list, int n, cudaStream_t st) {
+                if (n <= 0) return;
+                KTimer t(h, kid, st);
+                if (stage == 1) k_cell_lf1<1><<<nblk(n, 256), 256, 0, st>>>(h->P, Wc, Ui, Uo, Wo, list, n);
+                else            k_cell_lf1<2><<<nblk(n, 256), 256, 0, st>>>(h->P, Wc, Ui, Uo, Wo, list, n);
+            };
+            if (!multi) { sweep(nullptr, h->nc, S); continue; }
+            if (ov) { cudaEventRecord(h->ev_stage, S); cudaStreamWaitEvent(C, h->ev_stage, 0); }   // fork
+            if (stage == 2 && (rc = exchange_U(h, h->Ub, h->Wb, C))) return rc;    // halo copy of the stage-1 result
+            sweep(h->d_cells_bnd, h->n_cells_bnd, C);
+            if (ov) cudaEventRecord(h->ev_U, C);
+            sweep(h->d_cells_int, h->n_cells_int, S);
+            if (ov) cudaStreamWaitEvent(S, h->ev_U, 0);                               // join
+        }
+        if (multi) {
+            if (ov) { cudaEventRecord(h->ev_stage, S); cudaStreamWaitEvent(C, h->ev_stage, 0); }
+            if ((rc = exchange_U(h, h->Ua, h->W, C))) return rc;
+            if (ov) { cudaEventRecord(h->ev_U, C); cudaStreamWaitEvent(S, h->ev_U, 0); }
         }
         launch_remediate(h);
         return 0;
@@ -678,9 +701,9 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     h->pm.reset(new HostMesh(std::move(pm)));
     const HostMesh& pmr = *h->pm;
     if (h->fused) TRY(build_fused_plan(h));
+    h->lf1_cell = (c->flux == CFD2D_FLUX_LAX && c->order == 1);
+    if (const char* ev = getenv("CFD2D_LF1_CELL")) h->lf1_cell = h->lf1_cell && atoi(ev) != 0;
     if (!(halo && halo->nranks > 1)) {
-        h->lf1_cell = (c->flux == CFD2D_FLUX_LAX && c->order == 1);
-        if (const char* ev = getenv("CFD2D_LF1_CELL")) h->lf1_cell = h->lf1_cell && atoi(ev) != 0;
         if (const char* ev = getenv("CFD2D_DIAG_SPLIT")) h->diag_split = atoi(ev) != 0;
         if (h->diag_split) {
             std::vector<int> ci(nc);

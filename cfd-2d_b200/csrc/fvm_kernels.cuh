@@ -334,9 +334,11 @@ __global__ void __launch_bounds__(256) k_update(KParams P, const double4* __rest
 #endif
 template <int STAGE>
 __global__ void __launch_bounds__(256, CFD2D_LF1_MINB) k_cell_lf1(KParams P, const double4* __restrict__ W, const double4* Uin, double4* Uout,
-                                                  double4* __restrict__ Wout) {
+                                                  double4* __restrict__ Wout, const int* __restrict__ list, int n) {
+    // `list` (optional): only these n cells (multi-rank: cells without / with a halo neighbour)
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.nc) return;
+    if (c >= n) return;
+    if (list) c = __ldg(list + c);
     unsigned int fl = P.flag[c];
     if (fl & 2u) {                       // cellIsLim: frozen until remediated (:368, :421, :432)
         st4(Wout, c, ld4(W, c));
