@@ -61,3 +61,21 @@ def test_create_rejects_bad_arguments():
     with pytest.raises(fvm.CFDError) as e:
         fvm.Solver(m2, c.task)
     assert e.value.code == -5          # CFD2D_EBC, fvm_tvd.cpp:706-710
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the
+    contract's keys, the reference's own single-thread rate as `value`, zero copy bytes in `e2e`."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads(r.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["unit"] == "cell-updates/s" and d["higher_is_better"] is True
+    assert d["value"] > 1e5 and d["dtype"] == "f64"
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] == 1 and cb["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"]
