@@ -6,6 +6,7 @@
 #include "fvm_fused.cuh"
 #include "halo_nccl.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -568,6 +569,18 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         for (int e = 0; e < ne; e++) if (!(pm.edge_c1[e] >= nc || pm.edge_c2[e] >= nc)) ids.push_back(e);
         h->ne_int = (int)ids.size();
         for (int e = 0; e < ne; e++) if (pm.edge_c1[e] >= nc || pm.edge_c2[e] >= nc) ids.push_back(e);
+        // optional: visit edges in the order of their c1 cell on the device (Hilbert order) instead of the
+        // caller's edge order, so that consecutive edges gather neighbouring cell records
+        int edge_sort = 0;
+        if (const char* ev = getenv("CFD2D_EDGE_SORT")) edge_sort = atoi(ev);
+        if (edge_sort) {
+            auto by_cell = [&](int a, int b) {
+                int ka = pm.edge_c1[a], kb = pm.edge_c1[b];
+                return ka != kb ? ka < kb : a < b;
+            };
+            std::sort(ids.begin(), ids.begin() + h->ne_int, by_cell);
+            std::sort(ids.begin() + h->ne_int, ids.end(), by_cell);
+        }
         if (EDGE_TILE <= 0) { for (int q = 0; q < ne; q++) { order[q] = ids[q]; epos[ids[q]] = q; } }
         else {
             const int seg_beg[2] = {0, h->ne_int}, seg_end[2] = {h->ne_int, ne};
