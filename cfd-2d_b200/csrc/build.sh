@@ -10,5 +10,5 @@ $NVCC $FLAGS -c halo_nccl.cu -o halo_nccl.o
 ${CXX:-g++} -O2 -std=c++17 -fPIC -c unv_reader.cpp -o unv_reader.o
 OUT=${CFD2D_OUT:-libcfd2d_b200.so}
 $NVCC -shared -o $OUT fvm_api.o halo_nccl.o unv_reader.o -lcudart -ldl
-grep -E "Compiling entry|registers|spill" ptxas_fvm_api.log | paste - - - | sed -E 's/ptxas info\s+: //g' | awk '{print}' > ptxas_summary.txt || true
+grep -E "Compiling entry|registers|spill" ptxas_fvm_api.log | paste - - - | sed -E 's/ptxas info\s+: //g' | sort > ptxas_summary.txt || true
 echo "built $(pwd)/$OUT"
