@@ -9,7 +9,7 @@ SRC=$REF/src
 [ -f "$SRC/methods/fvm_tvd.cpp" ] || { echo "reference tree not found at $REF"; exit 1; }
 mkdir -p _build/obj
 CXX=${CXX:-g++}
-FL="-std=c++11 -O2 -fPIC -fpermissive -w -ffp-contract=off -I../../oracle/mpi_shim -I$SRC -I$SRC/methods -I$SRC/mesh -I$SRC/tinyxml"
+FL="-std=c++11 -O2 -fPIC -fpermissive -w -ffp-contract=off -Impi_shim -I$SRC -I$SRC/methods -I$SRC/mesh -I$SRC/tinyxml"
 for f in global bnd_cond mesh/grid mesh/MeshReader mesh/MeshReaderBerkleyTriangle mesh/MeshReaderSalomeUnv \
          methods/fvm_tvd tinyxml/tinystr tinyxml/tinyxml tinyxml/tinyxmlerror tinyxml/tinyxmlparser; do
   o=_build/obj/$(echo $f | tr / _).o

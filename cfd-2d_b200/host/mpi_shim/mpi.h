@@ -1,0 +1,32 @@
+/* Single-rank stand-in for <mpi.h>, TEST INFRASTRUCTURE ONLY.
+ *
+ * The reference (zhrv/cfd-2d) includes "mpi.h" from src/global.h:9 and calls a
+ * handful of MPI entry points from src/global.cpp:595-659.  The explicit FVM
+ * path (FVM_TVD) never communicates, so to compile the reference sources where
+ * they lie we only need the declarations.  Every function is a one-rank no-op.
+ */
+#ifndef CFD2D_ORACLE_MPI_SHIM_H
+#define CFD2D_ORACLE_MPI_SHIM_H
+typedef int MPI_Comm;
+typedef int MPI_Datatype;
+typedef int MPI_Op;
+typedef struct { int unused; } MPI_Status;
+#define MPI_COMM_WORLD 0
+#define MPI_DOUBLE 1
+#define MPI_INT 2
+#define MPI_MIN 3
+#define MPI_SUCCESS 0
+static inline int MPI_Init(int*, char***) { return 0; }
+static inline int MPI_Finalize(void) { return 0; }
+static inline int MPI_Comm_size(MPI_Comm, int* n) { *n = 1; return 0; }
+static inline int MPI_Comm_rank(MPI_Comm, int* r) { *r = 0; return 0; }
+static inline int MPI_Barrier(MPI_Comm) { return 0; }
+static inline int MPI_Send(const void*, int, MPI_Datatype, int, int, MPI_Comm) { return 0; }
+static inline int MPI_Recv(void*, int, MPI_Datatype, int, int, MPI_Comm, MPI_Status*) { return 0; }
+static inline int MPI_Allreduce(const void* s, void* r, int n, MPI_Datatype t, MPI_Op, MPI_Comm) {
+    const char* a = (const char*)s; char* b = (char*)r;
+    int w = (t == MPI_DOUBLE) ? 8 : 4;
+    for (int i = 0; i < n * w; i++) b[i] = a[i];
+    return 0;
+}
+#endif

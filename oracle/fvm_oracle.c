@@ -2,7 +2,7 @@
  *
  * CPU restatement, in plain C99, of the explicit finite-volume path of zhrv/cfd-2d
  * (class FVM_TVD).  It is the checker the CUDA path is compared with on the GPU box, where
- * /root/reference does not exist.  PARITY IS PINNED: tests/test_oracle_vs_reference.py and
+ * /root/reference does not exist.  PARITY IS PINNED: tests/test_oracle_golden.py (against the committed golden vectors) and
  * oracle/make_golden.py compare every function below BIT FOR BIT with the real reference
  * compiled from /root/reference (oracle/_ref, oracle/ref_harness.cpp); the golden vectors those
  * runs produce are committed under tests/golden/.  (The reference itself ships no tests or
