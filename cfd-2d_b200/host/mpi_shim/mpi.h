@@ -1,12 +1,13 @@
-/* Single-rank stand-in for <mpi.h>, TEST INFRASTRUCTURE ONLY.
+/* Single-rank stand-in for <mpi.h> for building the drop-in driver (cfd2d_cuda) where no MPI is
+ * installed; a site with MPI compiles the glue against its real <mpi.h> instead.
  *
  * The reference (zhrv/cfd-2d) includes "mpi.h" from src/global.h:9 and calls a
  * handful of MPI entry points from src/global.cpp:595-659.  The explicit FVM
  * path (FVM_TVD) never communicates, so to compile the reference sources where
  * they lie we only need the declarations.  Every function is a one-rank no-op.
  */
-#ifndef CFD2D_ORACLE_MPI_SHIM_H
-#define CFD2D_ORACLE_MPI_SHIM_H
+#ifndef CFD2D_HOST_MPI_SHIM_H
+#define CFD2D_HOST_MPI_SHIM_H
 typedef int MPI_Comm;
 typedef int MPI_Datatype;
 typedef int MPI_Op;
