@@ -102,6 +102,14 @@ static int dev_upload(cfd2d_fvm* h, const T** p, const std::vector<T>& v) {
     return 0;
 }
 
+// CUDA status -> CFD2D code with the message kept on the handle (create() pairs it with TRY, which
+// destroys the half-built handle)
+static int cuda_rc(cfd2d_fvm* h, cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    h->error = std::string(what) + " failed: " + cudaGetErrorString(e);
+    return CFD2D_ECUDA;
+}
+
 static inline int nblk(long long n, int t) { return (int)((n + t - 1) / t); }
 
 // rim_orig's constants, by the reference's own expressions (global.cpp:235-249)
@@ -771,13 +779,13 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         {   // highest priority: the small pack / NCCL kernels must not queue behind a full-GPU sweep
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
-            CUDA_TRY(h, cudaStreamCreateWithPriority(&h->comm, cudaStreamNonBlocking, hi));
+            TRY(cuda_rc(h, cudaStreamCreateWithPriority(&h->comm, cudaStreamNonBlocking, hi), "cudaStreamCreateWithPriority"));
         }
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_G, cudaEventDisableTiming));
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming));
-        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_U, cudaEventDisableTiming));
+        TRY(cuda_rc(h, cudaEventCreateWithFlags(&h->ev_G, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
+        TRY(cuda_rc(h, cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
+        TRY(cuda_rc(h, cudaEventCreateWithFlags(&h->ev_U, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
     }
-    CUDA_TRY(h, cudaDeviceSynchronize());
+    TRY(cuda_rc(h, cudaDeviceSynchronize(), "cudaDeviceSynchronize (create)"));
 #undef TRY
     *out = h;
     return CFD2D_OK;
