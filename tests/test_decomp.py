@@ -198,3 +198,26 @@ def test_slab_window_equals_global_decomposition(world):
         st = c.smooth_state(tiles=world, extent=(0.0, float(world * nx), 0.0, float(ny)))
         for a, b in zip(st, gst):
             assert np.array_equal(a[rm.g_cells[:rm.nc]], b[ref.g_cells[:ref.nc]])
+
+
+def test_slab_window_send_recv_lists_pair_up():
+    """What rank r packs for rank p (in order) is exactly what p expects in its halo slice from r:
+    checked geometrically (cell centres), since window meshes number their cells independently."""
+    world, nx, ny = 4, 10, 5
+    rms = []
+    for r in range(world):
+        c, rm = decomp.slab_rank_mesh(nx, ny, r, world)
+        rms.append((c, rm))
+    for r, (c, rm) in enumerate(rms):
+        shift = np.concatenate([[0], np.cumsum(rm.recv_count)])
+        for p in range(world):
+            cp, rp = rms[p]
+            sent = np.asarray(rp.send_ind[r], dtype=np.int64)           # p's owned cells sent to r, in order
+            assert sent.shape[0] == rm.recv_count[p]
+            if not sent.shape[0]:
+                continue
+            halo = np.arange(rm.nc + shift[p], rm.nc + shift[p + 1])     # r's halo slice for p
+            sx, sy = rp.local["cell_cx"][sent], rp.local["cell_cy"][sent]
+            hx, hy = rm.local["cell_cx"][halo], rm.local["cell_cy"][halo]
+            assert np.array_equal(sx, hx) and np.array_equal(sy, hy)
+            assert np.array_equal(rp.local["cell_S"][sent], rm.local["cell_S"][halo])
