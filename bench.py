@@ -258,6 +258,10 @@ def main():
                     help="N>1: strong scaling -- the (nx x ny x 2)-cell mesh is the WHOLE job, split N ways "
                          "(BASELINE configs[3]: --nx 8000 --ny 2000 = 32 M cells); default is weak scaling (nx x ny x 2 per GPU)")
     ap.add_argument("--fused", action="store_true", help="one tile-fused kernel per stage (k_stage) instead of k_grad, k_flux, k_update")
+    ap.add_argument("--layout", type=int, default=None, choices=[0, 1, 2],
+                    help="step layout: 0 three sweeps, 1 k_stage, 2 k_stage_pipe (persistent, cp.async.bulk-fed); default: the library's")
+    ap.add_argument("--exact-riemann", action="store_true",
+                    help="Godunov: rim_orig in the reference's operation order instead of the reduced-instruction solver")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference_arm(a)
@@ -298,8 +302,12 @@ def main():
         s, st, nc_local, nc_total = decomp.make_rank_solver(nx_rank, a.ny, rank, world, local, flux, a.order, dist,
                                                             partition=a.partition,
                                                             tiles=max(1, a.nx // 1000) if a.strong else None)
-    if a.fused:
-        s.use_fused(True)
+    if a.fused and a.layout is None:
+        a.layout = 1
+    if a.layout is not None:
+        s.use_fused(a.layout)
+    if a.exact_riemann:
+        s.use_exact_riemann(True)
     stream = torch.cuda.Stream()          # a real (capturable) stream; torch events are recorded on it
     torch.cuda.set_stream(stream)
     s.set_stream(stream.cuda_stream)
@@ -432,8 +440,8 @@ def main():
         variants = {}
         for name, (vf, vo) in {"lax_order2": (1, 2), "lax_order1": (1, 1)}.items():
             s2 = fvm.Solver(c.mesh, c.task, vf, vo, device=local)
-            if a.fused:
-                s2.use_fused(True)
+            if a.layout is not None:
+                s2.use_fused(a.layout)
             s2.set_stream(stream.cuda_stream)
             s2.set_state(*st)
             s2.calc_time_step()

@@ -4,6 +4,7 @@
 #include "../../include/cfd2d_fvm.h"
 #include "fvm_kernels.cuh"
 #include "fvm_fused.cuh"
+#include "fvm_pipe.cuh"
 #include "halo_nccl.h"
 
 #include <algorithm>
@@ -30,15 +31,29 @@ struct cfd2d_fvm {
     std::vector<void*> allocs;
     double4 *Ua = nullptr, *Ub = nullptr, *W = nullptr, *Wb = nullptr, *G = nullptr, *F = nullptr;
     uint32_t* io_u32 = nullptr;   // flag staging (caller order)
+    double* grad_tmp = nullptr;   // parity hook staging (cfd2d_fvm_calc_grad), allocated on first use
     // tile-fused stage kernel (fvm_fused.cuh)
     bool fused = true;
     FParams Q{};
     int ntiles = 0, n_interior = 0, n_boundary = 0, stage_nt = 256;
     size_t stage_smem = 0;
     int *d_interior = nullptr, *d_boundary = nullptr;
+    // pipelined tile kernel (fvm_pipe.cuh)
+    bool pipe = false;            // step layout 2: k_stage_pipe
+    bool have_pipe_plan = false;
+    bool w_stale = false;         // the pipe layout does not maintain the primitive cache W
+    PParams PQ{};
+    int pipe_nt = 256, pipe_minb = 2, pipe_grid = 0, pipe_ntiles = 0, pipe_n_interior = 0, pipe_n_boundary = 0;
+    size_t pipe_smem = 0;
+    int *d_pipe_interior = nullptr, *d_pipe_boundary = nullptr;
+    int* d_near_send = nullptr;   // multi-rank pipe layout: owned cells within one ring of a send cell (W refresh list)
+    int n_near_send = 0;
+    int sm_count = 0;
     bool overlap = true;          // multi-rank: halo exchange on the comm stream, overlapped with interior work
+    bool exact_riemann = false;   // Godunov: true = rim_orig_dev (the reference's operation order), false = fvm_riemann_fast.cuh
     bool lf1_cell = false;        // first-order Lax-Friedrichs: one cell-parallel sweep per stage (k_cell_lf1)
     bool diag_split = false;      // diagnostics only (CFD2D_DIAG_SPLIT=1): serial handle runs the multi-rank kernel split
+    bool collective_errors = true; // multi-rank: sync() all-reduces the Newton-cap error word (CFD2D_COLLECTIVE_ERRORS=0: rank-local)
     bool skip_exchange = false;   // diagnostics only (CFD2D_DIAG_NO_EXCHANGE=1): results are wrong, timing shows the cost of the exchanges
     int ne_int = 0;               // device edges [0, ne_int) touch owned cells only; [ne_int, ne) touch a halo cell
     int *d_cells_int = nullptr, *d_cells_bnd = nullptr;   // owned cells without / with a halo neighbour
@@ -130,6 +145,8 @@ static RimC make_rim(double GAM) {
     k.IAGAM = (1 / k.AGAM);
     k.DG1 = (1 + k.DGAM);
     k.DGGG = k.DGAM * k.GGAM;
+    k.ISGAM = 1.0 / k.SGAM;
+    k.IDG1 = 1.0 / k.DG1;
     return k;
 }
 
@@ -175,7 +192,11 @@ static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale, int e0 = 0
     KTimer t(h, CFD2D_K_FLUX, st);
     dim3 g(nblk(2 * (long long)(e1 - e0), 128)), b(128);   // one thread per (edge, Gauss point)
     int fx = h->ctrl.flux, od = h->ctrl.order;
-    if (fx == CFD2D_FLUX_GODUNOV && od == 2) k_flux<0, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
+    if (fx == CFD2D_FLUX_GODUNOV && !h->exact_riemann) {
+        if (od == 2) k_flux<2, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
+        else k_flux<2, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
+    }
+    else if (fx == CFD2D_FLUX_GODUNOV && od == 2) k_flux<0, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
     else if (fx == CFD2D_FLUX_GODUNOV) k_flux<0, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
     else if (od == 2) k_flux<1, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
     else k_flux<1, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
@@ -190,7 +211,8 @@ static void launch_update(cfd2d_fvm* h, int stage) {
 
 static void launch_remediate(cfd2d_fvm* h) {
     KTimer t(h, CFD2D_K_REMEDIATE);
-    k_remediate<<<1, 1024, 0, h->stream>>>(h->P, h->Ua, h->W);
+    // Ub (the stage-1 state) and G are dead at the end of a step: snapshot / staging space of the sweep
+    k_remediate<<<1, 1024, 0, h->stream>>>(h->P, h->Ua, h->Ub, h->W, h->G);
 }
 
 static void launch_tau_steady(cfd2d_fvm* h) {
@@ -208,16 +230,25 @@ static stage_fn stage_kernel_nt(int flux, int order, int stage) {
         if (order == 2) return stage == 1 ? (stage_fn)k_stage<0, 2, 1, NT, MINB> : (stage_fn)k_stage<0, 2, 2, NT, MINB>;
         return stage == 1 ? (stage_fn)k_stage<0, 1, 1, NT, MINB> : (stage_fn)k_stage<0, 1, 2, NT, MINB>;
     }
+    if (flux == 2) {    // Godunov through the reduced-instruction solver
+        if (order == 2) return stage == 1 ? (stage_fn)k_stage<2, 2, 1, NT, MINB> : (stage_fn)k_stage<2, 2, 2, NT, MINB>;
+        return stage == 1 ? (stage_fn)k_stage<2, 1, 1, NT, MINB> : (stage_fn)k_stage<2, 1, 2, NT, MINB>;
+    }
     if (order == 2) return stage == 1 ? (stage_fn)k_stage<1, 2, 1, NT, MINB> : (stage_fn)k_stage<1, 2, 2, NT, MINB>;
     return stage == 1 ? (stage_fn)k_stage<1, 1, 1, NT, MINB> : (stage_fn)k_stage<1, 1, 2, NT, MINB>;
 }
 
+static int flux_variant(const cfd2d_fvm* h) {   // template FLUX value: 0 Godunov bit-faithful, 1 LF, 2 Godunov reduced-instruction
+    return (h->ctrl.flux == CFD2D_FLUX_GODUNOV && !h->exact_riemann) ? 2 : h->ctrl.flux;
+}
+
 static stage_fn stage_kernel(const cfd2d_fvm* h, int stage) {
+    const int fx = flux_variant(h);
     switch (h->stage_nt) {
-        case 128: return stage_kernel_nt<128, 8>(h->ctrl.flux, h->ctrl.order, stage);
-        case 384: return stage_kernel_nt<384, 2>(h->ctrl.flux, h->ctrl.order, stage);
-        case 512: return stage_kernel_nt<512, 2>(h->ctrl.flux, h->ctrl.order, stage);
-        default:  return stage_kernel_nt<256, 4>(h->ctrl.flux, h->ctrl.order, stage);
+        case 128: return stage_kernel_nt<128, 8>(fx, h->ctrl.order, stage);
+        case 384: return stage_kernel_nt<384, 2>(fx, h->ctrl.order, stage);
+        case 512: return stage_kernel_nt<512, 2>(fx, h->ctrl.order, stage);
+        default:  return stage_kernel_nt<256, 4>(fx, h->ctrl.order, stage);
     }
 }
 
@@ -287,7 +318,9 @@ static int enqueue_step_unfused(cfd2d_fvm* h) {
             };
             if (!multi) { sweep(nullptr, h->nc, S); continue; }
             if (ov) { cudaEventRecord(h->ev_stage, S); cudaStreamWaitEvent(C, h->ev_stage, 0); }   // fork
-            if (stage == 2 && (rc = exchange_U(h, h->Ub, h->Wb, C))) return rc;    // halo copy of the stage-1 result
+            // halo copy of the state this stage starts from: stage 2 = the stage-1 result; stage 1 = Ua again,
+            // because remediateLimCells may have rewritten send cells after the end-of-step exchange
+            if ((rc = exchange_U(h, Ui, stage == 1 ? h->W : h->Wb, C))) return rc;
             sweep(h->d_cells_bnd, h->n_cells_bnd, C);
             if (ov) cudaEventRecord(h->ev_U, C);
             sweep(h->d_cells_int, h->n_cells_int, S);
@@ -308,7 +341,11 @@ static int enqueue_step_unfused(cfd2d_fvm* h) {
             launch_flux(h, Ucur, 1);
         } else {
             if (ov) { cudaEventRecord(h->ev_stage, S); cudaStreamWaitEvent(C, h->ev_stage, 0); }   // fork
-            if (stage == 2 && (rc = exchange_U(h, Ucur, h->W, C))) return rc;     // halo copy of the stage-1 result
+            // halo copy of the state this stage starts from (hidden behind the interior gradient sweep).
+            // Stage 1 re-sends Ua: remediateLimCells (end of the previous step) may have rewritten send
+            // cells AFTER the end-of-step exchange, and the peers' stage-1 gradients/fluxes must see them
+            // (the serial reference sweeps every cell before the next step, fvm_tvd.cpp:449).
+            if ((rc = exchange_U(h, Ucur, h->W, C))) return rc;
             if (o2) {
                 launch_grad(h, h->d_cells_bnd, h->n_cells_bnd, C);
                 if (ov) cudaEventRecord(h->ev_G, C);
@@ -354,6 +391,8 @@ static int enqueue_step_fused(cfd2d_fvm* h) {
         // exchange) is complete
         cudaEventRecord(h->ev_stage, h->stream);
         cudaStreamWaitEvent(h->comm, h->ev_stage, 0);
+        // cells remediated at the end of the previous step -> peers (see enqueue_step_unfused)
+        if (stage == 1 && (rc = exchange_U(h, h->Ua, h->W, h->comm))) return rc;
         if (h->ctrl.order == 2) {
             if (h->n_send > 0) {
                 h->launches++;
@@ -381,7 +420,106 @@ static int enqueue_step_fused(cfd2d_fvm* h) {
     return 0;
 }
 
-static int enqueue_step(cfd2d_fvm* h) { return h->fused ? enqueue_step_fused(h) : enqueue_step_unfused(h); }
+// ---- the pipelined tile kernel: template dispatch over (flux, order, stage, block size) ---------
+typedef void (*pipe_fn)(KParams, PParams, const double4*, double4*, const double4*);
+
+template <int NT, int MINB>
+static pipe_fn pipe_kernel_nt(int flux, int order, int stage) {
+    if (flux == CFD2D_FLUX_GODUNOV) {
+        if (order == 2) return stage == 1 ? (pipe_fn)k_stage_pipe<0, 2, 1, NT, MINB> : (pipe_fn)k_stage_pipe<0, 2, 2, NT, MINB>;
+        return stage == 1 ? (pipe_fn)k_stage_pipe<0, 1, 1, NT, MINB> : (pipe_fn)k_stage_pipe<0, 1, 2, NT, MINB>;
+    }
+    if (flux == 2) {
+        if (order == 2) return stage == 1 ? (pipe_fn)k_stage_pipe<2, 2, 1, NT, MINB> : (pipe_fn)k_stage_pipe<2, 2, 2, NT, MINB>;
+        return stage == 1 ? (pipe_fn)k_stage_pipe<2, 1, 1, NT, MINB> : (pipe_fn)k_stage_pipe<2, 1, 2, NT, MINB>;
+    }
+    if (order == 2) return stage == 1 ? (pipe_fn)k_stage_pipe<1, 2, 1, NT, MINB> : (pipe_fn)k_stage_pipe<1, 2, 2, NT, MINB>;
+    return stage == 1 ? (pipe_fn)k_stage_pipe<1, 1, 1, NT, MINB> : (pipe_fn)k_stage_pipe<1, 1, 2, NT, MINB>;
+}
+
+static pipe_fn pipe_kernel(const cfd2d_fvm* h, int stage) {
+    const int fx = flux_variant(h);
+    switch (h->pipe_nt) {
+        case 128: return pipe_kernel_nt<128, 4>(fx, h->ctrl.order, stage);
+        case 384: return pipe_kernel_nt<384, 1>(fx, h->ctrl.order, stage);
+        case 512: return pipe_kernel_nt<512, 1>(fx, h->ctrl.order, stage);
+        default:  return pipe_kernel_nt<256, 2>(fx, h->ctrl.order, stage);
+    }
+}
+
+// tiles: nullptr = all tiles, else a list of n tile ids.  Persistent launch: at most one wave of CTAs.
+static void launch_pipe(cfd2d_fvm* h, int stage, const int* tiles, int n, cudaStream_t st = nullptr) {
+    if (n <= 0) return;
+    if (!st) st = h->stream;
+    KTimer t(h, stage == 1 ? CFD2D_K_STAGE1 : CFD2D_K_STAGE2, st);
+    PParams q = h->PQ;
+    q.tile_ids = tiles;
+    q.n_tiles = n;
+    const int grid = n < h->pipe_grid ? n : h->pipe_grid;
+    pipe_fn f = pipe_kernel(h, stage);
+    if (stage == 1) f<<<grid, h->pipe_nt, h->pipe_smem, st>>>(h->P, q, h->Ua, h->Ub, h->G);
+    else            f<<<grid, h->pipe_nt, h->pipe_smem, st>>>(h->P, q, h->Ub, h->Ua, h->G);
+}
+
+// The step with the pipelined tile kernel: 3 launches (k_stage_pipe x 2, k_remediate); W is not
+// maintained (w_stale).  Multi-rank handles: per stage the comm stream refreshes the state halo,
+// converts the cells around the send set to primitive form, computes and exchanges the gradients of
+// the send cells; interior tiles (no rank-halo data within two rings) run meanwhile, boundary tiles
+// after the gradient exchange.
+static int enqueue_step_pipe(cfd2d_fvm* h) {
+    int rc;
+    if (h->ctrl.steady) {                                    // calcTimeStep reads the primitive state (:315)
+        launch_prim(h, h->Ua, h->W, 0, h->nc, h->stream);
+        launch_tau_steady(h);
+    }
+    if (!h->halo) {
+        launch_pipe(h, 1, nullptr, h->pipe_ntiles);
+        launch_pipe(h, 2, nullptr, h->pipe_ntiles);
+        launch_remediate(h);
+        return 0;
+    }
+    for (int stage = 1; stage <= 2; stage++) {
+        double4* Ucur = stage == 1 ? h->Ua : h->Ub;
+        cudaEventRecord(h->ev_stage, h->stream);
+        cudaStreamWaitEvent(h->comm, h->ev_stage, 0);
+        if ((rc = exchange_U(h, Ucur, h->W, h->comm))) return rc;        // halo U (+ halo W for the send cells' gradients)
+        if (h->ctrl.order == 2) {
+            if (h->n_near_send > 0) {
+                h->launches++;
+                k_prim_list<<<nblk(h->n_near_send, 256), 256, 0, h->comm>>>(h->P, Ucur, h->W, h->d_near_send, h->n_near_send);
+            }
+            if (h->n_send > 0) {
+                h->launches++;
+                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, h->W, h->G, h->d_send_dev, h->n_send);
+            }
+            if ((rc = exchange_G(h, h->comm))) return rc;
+        }
+        cudaEventRecord(h->ev_G, h->comm);
+        launch_pipe(h, stage, h->d_pipe_interior, h->pipe_n_interior);
+        cudaStreamWaitEvent(h->stream, h->ev_G, 0);
+        launch_pipe(h, stage, h->d_pipe_boundary, h->pipe_n_boundary);
+    }
+    // remediateLimCells reads neighbour states, possibly halo cells: the end-of-step exchange first
+    cudaEventRecord(h->ev_stage, h->stream);
+    cudaStreamWaitEvent(h->comm, h->ev_stage, 0);
+    if ((rc = exchange_U(h, h->Ua, h->W, h->comm))) return rc;
+    cudaEventRecord(h->ev_U, h->comm);
+    cudaStreamWaitEvent(h->stream, h->ev_U, 0);
+    launch_remediate(h);
+    return 0;
+}
+
+static int enqueue_step(cfd2d_fvm* h) {
+    if (h->pipe) { h->w_stale = true; return enqueue_step_pipe(h); }
+    return h->fused ? enqueue_step_fused(h) : enqueue_step_unfused(h);
+}
+
+// consumers of the primitive cache outside the step (time step, parity hooks, layout switches)
+static void ensure_W(cfd2d_fvm* h) {
+    if (!h->w_stale) return;
+    launch_prim(h, h->Ua, h->W, 0, h->nc_ex, h->stream);
+    h->w_stale = false;
+}
 
 static void drop_graph(cfd2d_fvm* h) {
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -392,6 +530,14 @@ static int check_device_errors(cfd2d_fvm* h) {
     int e[2] = {0, 0};
     CUDA_TRY(h, cudaMemcpyAsync(e, h->err, sizeof e, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->halo && h->collective_errors) {
+        // a rank that stops stepping would leave its peers blocked in the next ncclSend/Recv: every rank
+        // learns the worst count (MPI_Allreduce analogue, fem_rkdg.cpp:413) and returns the same code
+        double worst = -(double)e[0];
+        int rc = halo_allreduce_min(h->halo, &worst, h->comm);
+        if (rc) { h->error = halo_error(h->halo); return rc; }
+        if (worst < 0.0 && e[0] == 0) e[0] = (int)(-worst);
+    }
     if (e[0] != 0) {
         char b[256];
         snprintf(b, sizeof b, "rim_orig Newton iteration hit the cap (%d) on %d edge evaluations: non-physical "
@@ -473,6 +619,102 @@ static int build_fused_plan(cfd2d_fvm* h) {
     }
 #undef FTRY
     h->have_plan = true;
+    return 0;
+}
+
+// Host plan + device tables of the pipelined tile kernel (fvm_tiling.h build_pipe_plan, fvm_pipe.cuh)
+static int build_pipe_plan_dev(cfd2d_fvm* h) {
+    if (h->have_pipe_plan) return 0;
+    if (!h->pm) { h->error = "internal: host mesh released"; return CFD2D_EINVAL; }
+    int rc = 0;
+#define FTRY(x) do { rc = (x); if (rc) return rc; } while (0)
+    int TC = 128;
+    if (const char* ev = getenv("CFD2D_PIPE_TILE")) TC = atoi(ev);
+    h->pipe_nt = 256;
+    if (const char* ev = getenv("CFD2D_PIPE_NT")) h->pipe_nt = atoi(ev);
+    if (h->pipe_nt != 128 && h->pipe_nt != 256 && h->pipe_nt != 384 && h->pipe_nt != 512) h->pipe_nt = 256;
+    h->pipe_minb = h->pipe_nt == 128 ? 4 : (h->pipe_nt == 256 ? 2 : 1);
+    PipePlan pp;
+    // Godunov: edges of a tile grouped by normal direction (branch coherence of rim_orig); LF: by cell id
+    std::string perr = build_pipe_plan(*h->pm, TC, h->ctrl.flux == CFD2D_FLUX_GODUNOV, pp);
+    if (!perr.empty()) { h->error = perr; return CFD2D_EINVAL; }
+    h->pipe_ntiles = pp.ntiles;
+    h->pipe_n_interior = (int)pp.interior.size();
+    h->pipe_n_boundary = (int)pp.boundary.size();
+    PParams& Q = h->PQ;
+    Q.tile_ids = nullptr; Q.n_tiles = pp.ntiles;
+    FTRY(dev_upload(h, &Q.tiles, pp.tiles));
+    FTRY(dev_upload(h, &Q.ring, pp.ring));
+    FTRY(dev_upload(h, &Q.blob, pp.blob));
+    Q.c_orig = h->P.c_orig;
+    { const int* q = nullptr; FTRY(dev_upload(h, &q, pp.interior)); h->d_pipe_interior = (int*)q; }
+    { const int* q = nullptr; FTRY(dev_upload(h, &q, pp.boundary)); h->d_pipe_boundary = (int*)q; }
+    auto up = [](long long x, long long a) { return (int)((x + a - 1) / a * a); };
+    const int TCp = pp.TC;
+    int o = 0;
+    o = up(pp.blob_max, 128);
+    Q.so_u = o; o += 32 * TCp;
+    Q.so_uold = o; o += 32 * TCp;
+    Q.so_cfl = o; o += up(8LL * TCp + 16, 16);
+    Q.so_flag = o; o += up(4LL * TCp + 16, 16);
+    Q.so_ring = o; o += 32 * (pp.nring_max > 0 ? pp.nring_max : 1);
+    Q.so_gx = o; o += 64 * (pp.nhalo_max > 0 ? pp.nhalo_max : 1);
+    Q.stage_bytes = up(o, 128);
+    Q.o_stage0 = 128;
+    int q = Q.o_stage0 + 2 * Q.stage_bytes;
+    Q.nl2_max = pp.nl2_max; Q.nl_max = pp.nl_max; Q.ne_max = pp.ne_max;
+    Q.o_W0 = q; q += 16 * pp.nl2_max;
+    Q.o_W1 = q; q += 16 * pp.nl2_max;
+    Q.o_E = q; q += up(8LL * (h->ctrl.flux == CFD2D_FLUX_LAX ? pp.nl2_max : 0), 16);
+    Q.o_G = q; q += (h->ctrl.order == 2 ? 64 * pp.nl_max : 0);
+    Q.o_F = q; q += 32 * pp.ne_max;
+    h->pipe_smem = (size_t)q;
+    if (h->pipe_smem > 227 * 1024) { h->error = "pipe tile does not fit in shared memory (lower CFD2D_PIPE_TILE)"; return CFD2D_EINVAL; }
+    for (int fx = 0; fx < 2; fx++) {        // both Riemann variants of a Godunov handle
+        const bool keep = h->exact_riemann;
+        h->exact_riemann = fx != 0;
+        for (int st = 1; st <= 2; st++)
+            CUDA_TRY(h, cudaFuncSetAttribute((const void*)pipe_kernel(h, st), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->pipe_smem));
+        h->exact_riemann = keep;
+    }
+    {
+        cudaDeviceProp prop;
+        CUDA_TRY(h, cudaGetDeviceProperties(&prop, h->device));
+        h->sm_count = prop.multiProcessorCount;
+        int per_sm = 0;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)pipe_kernel(h, 2), h->pipe_nt, h->pipe_smem));
+        if (per_sm < 1) { h->error = "k_stage_pipe cannot be resident (registers / shared memory)"; return CFD2D_EINVAL; }
+        if (const char* ev = getenv("CFD2D_PIPE_CTAS")) { int v = atoi(ev); if (v > 0 && v < per_sm) per_sm = v; }
+        h->pipe_grid = h->sm_count * per_sm;          // persistent: one resident wave
+        char b[320];
+        snprintf(b, sizeof b, "pipe: tiles=%d (TC=%d, interior=%d, boundary=%d) nt=%d ctas/sm=%d grid=%d smem=%zu B (stage %d B, blob<=%d B) "
+                 "ring1/own=%.3f ring2/own=%.3f edges/own=%.3f blob B/cell=%.1f",
+                 pp.ntiles, pp.TC, h->pipe_n_interior, h->pipe_n_boundary, h->pipe_nt, per_sm, h->pipe_grid, h->pipe_smem, Q.stage_bytes, pp.blob_max,
+                 h->nc ? (double)pp.sum_ring1 / h->nc : 0.0, h->nc ? (double)pp.sum_ring2 / h->nc : 0.0, h->nc ? (double)pp.sum_ne / h->nc : 0.0,
+                 h->nc ? (double)pp.blob.size() / h->nc : 0.0);
+        h->plan_summary = b;
+    }
+    if (h->halo) {
+        // owned cells within one ring of a send cell: their W feeds k_grad(send list)
+        const HostMesh& pm = *h->pm;
+        std::vector<char> mark(h->nc, 0);
+        std::vector<int> send_dev(h->n_send > 0 ? h->n_send : 0);
+        if (h->n_send > 0) CUDA_TRY(h, cudaMemcpy(send_dev.data(), h->d_send_dev, (size_t)h->n_send * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int c : send_dev) {
+            mark[c] = 1;
+            for (int k = 0; k < 3; k++) {
+                const int e = pm.cell_edges[3 * (size_t)c + k];
+                const int nb = pm.edge_c1[e] == c ? pm.edge_c2[e] : pm.edge_c1[e];
+                if (nb >= 0 && nb < h->nc) mark[nb] = 1;
+            }
+        }
+        std::vector<int> near;
+        for (int c = 0; c < h->nc; c++) if (mark[c]) near.push_back(c);
+        h->n_near_send = (int)near.size();
+        { const int* q2 = nullptr; FTRY(dev_upload(h, &q2, near)); h->d_near_send = (int*)q2; }
+    }
+#undef FTRY
+    h->have_pipe_plan = true;
     return 0;
 }
 
@@ -689,9 +931,9 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     TRY(dev_upload(h, &P.e_d1, e_d1));
     TRY(dev_upload(h, &P.e_d2, e_d2));
     TRY(dev_upload(h, &P.e_bc, ebc));
-    TRY(dev_alloc(h, &P.cfl, (size_t)nc));
+    TRY(dev_alloc(h, &P.cfl, (size_t)nc + 2));      // + 16 bytes: the pipelined kernel's bulk copies are whole 16-byte units
     TRY(dev_alloc(h, &P.ctau, (size_t)nc));
-    TRY(dev_alloc(h, &P.flag, (size_t)nc));
+    TRY(dev_alloc(h, &P.flag, (size_t)nc + 4));
     TRY(dev_alloc(h, &h->err, 4));
     P.err = h->err;
     int cap = 1;
@@ -709,25 +951,33 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     TRY(dev_alloc(h, &h->F, (size_t)ne));
     for (int i = 0; i < 6; i++) TRY(dev_alloc(h, &h->io[i], (size_t)nc));
     TRY(dev_alloc(h, &h->tau_bits, 1));
-    cudaMemset(h->err, 0, 4 * sizeof(int));
-    cudaMemset(P.flag, 0, (size_t)(nc ? nc : 1) * sizeof(unsigned int));
-    cudaMemset(h->Ua, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
-    cudaMemset(h->Ub, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
-    cudaMemset(h->W, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
-    cudaMemset(h->Wb, 0, (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
-    cudaMemset(h->G, 0, 2 * (size_t)(nc_ex ? nc_ex : 1) * sizeof(double4));
-    cudaMemset(P.cfl, 0, (size_t)(nc ? nc : 1) * sizeof(double));
-    cudaMemset(P.ctau, 0, (size_t)(nc ? nc : 1) * sizeof(double));
+    TRY(dev_alloc(h, &P.rstat, (size_t)nc_ex));
+    {
+        const size_t n1 = nc ? nc : 1, nx = nc_ex ? nc_ex : 1;
+        TRY(cuda_rc(h, cudaMemset(h->err, 0, 4 * sizeof(int)), "cudaMemset(err)"));
+        TRY(cuda_rc(h, cudaMemset(P.flag, 0, n1 * sizeof(unsigned int)), "cudaMemset(flag)"));
+        TRY(cuda_rc(h, cudaMemset(P.rstat, 0, nx), "cudaMemset(rstat)"));
+        TRY(cuda_rc(h, cudaMemset(h->Ua, 0, nx * sizeof(double4)), "cudaMemset(Ua)"));
+        TRY(cuda_rc(h, cudaMemset(h->Ub, 0, nx * sizeof(double4)), "cudaMemset(Ub)"));
+        TRY(cuda_rc(h, cudaMemset(h->W, 0, nx * sizeof(double4)), "cudaMemset(W)"));
+        TRY(cuda_rc(h, cudaMemset(h->Wb, 0, nx * sizeof(double4)), "cudaMemset(Wb)"));
+        TRY(cuda_rc(h, cudaMemset(h->G, 0, 2 * nx * sizeof(double4)), "cudaMemset(G)"));
+        TRY(cuda_rc(h, cudaMemset(P.cfl, 0, n1 * sizeof(double)), "cudaMemset(cfl)"));
+        TRY(cuda_rc(h, cudaMemset(P.ctau, 0, n1 * sizeof(double)), "cudaMemset(ctau)"));
+    }
     // ---- step layout.  Default: three sweeps per stage.  Measured on B200 at 4 M cells
     // (profiles/README.md) the tile-fused kernel moves ~35 % fewer HBM bytes but its barrier-separated
     // phases expose more load latency than the three full-width sweeps hide; it stays selectable
     // (cfd2d_fvm_use_fused, CFD2D_FUSED=1) and is held to bit-identity with the sweeps by the tests.
     // Its plan (1-2 GB of tables at 4 M cells) is only built when it is selected.
     h->fused = false;
-    if (const char* ev = getenv("CFD2D_FUSED")) h->fused = atoi(ev) != 0;
+    int layout = 0;
+    if (const char* ev = getenv("CFD2D_FUSED")) layout = atoi(ev);
+    h->fused = layout == 1;
     h->pm.reset(new HostMesh(std::move(pm)));
     const HostMesh& pmr = *h->pm;
     if (h->fused) TRY(build_fused_plan(h));
+    if (const char* ev = getenv("CFD2D_EXACT_RIEMANN")) h->exact_riemann = atoi(ev) != 0;
     h->lf1_cell = (c->flux == CFD2D_FLUX_LAX && c->order == 1);
     if (const char* ev = getenv("CFD2D_LF1_CELL")) h->lf1_cell = h->lf1_cell && atoi(ev) != 0;
     if (!(halo && halo->nranks > 1)) {
@@ -749,6 +999,21 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
             int s = halo->send_ind[i];
             if (s < 0 || s >= nc) { g_create_error = "send_ind entry is not an owned cell"; cfd2d_fvm_destroy(h); return CFD2D_EINVAL; }
             send_dev[i] = h->perm[s];
+        }
+        // remediateLimCells across ranks: a flagged owned cell reads the PRE-remediation value of a halo
+        // c2-neighbour, which equals the serial ascending sweep iff that neighbour has the higher global
+        // id.  Decomp keeps the global edge orientation and the reference's readers create every edge from
+        // its lower-numbered cell, so c1 < c2 holds there; verify it when the global ids are given.
+        if (halo->cell_gid) {
+            for (int e = 0; e < ne; e++) {
+                const int a1 = m->edge_c1[e], a2 = m->edge_c2[e];
+                if (a2 >= 0 && (a1 >= nc || a2 >= nc) && !(halo->cell_gid[a1] < halo->cell_gid[a2])) {
+                    g_create_error = "multi-rank handle: an edge across the partition has global id(c1) > id(c2); "
+                                     "remediateLimCells would not equal the serial sweep (fvm_tvd.cpp:464-499)";
+                    cfd2d_fvm_destroy(h);
+                    return CFD2D_EINVAL;
+                }
+            }
         }
         cfd2d_halo hd = *halo;
         hd.send_ind = send_dev.data();
@@ -776,6 +1041,7 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         { const int* q = nullptr; TRY(dev_upload(h, &q, cb)); h->d_cells_bnd = (int*)q; }
         if (const char* ev = getenv("CFD2D_OVERLAP")) h->overlap = atoi(ev) != 0;
         if (const char* ev = getenv("CFD2D_DIAG_NO_EXCHANGE")) h->skip_exchange = atoi(ev) != 0;
+        if (const char* ev = getenv("CFD2D_COLLECTIVE_ERRORS")) h->collective_errors = atoi(ev) != 0;
         {   // highest priority: the small pack / NCCL kernels must not queue behind a full-GPU sweep
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -785,6 +1051,7 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         TRY(cuda_rc(h, cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
         TRY(cuda_rc(h, cudaEventCreateWithFlags(&h->ev_U, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
     }
+    if (layout == 2) { TRY(build_pipe_plan_dev(h)); h->pipe = true; }
     TRY(cuda_rc(h, cudaDeviceSynchronize(), "cudaDeviceSynchronize (create)"));
 #undef TRY
     *out = h;
@@ -832,8 +1099,25 @@ int cfd2d_fvm_use_fused(cfd2d_fvm* h, int on) {
     cudaStreamSynchronize(h->stream);
     if (h->comm) cudaStreamSynchronize(h->comm);
     drop_graph(h);
-    if (on) { int rc = build_fused_plan(h); if (rc) return rc; }
-    h->fused = on != 0;
+    if (on != 0 && on != 1 && on != 2) { h->error = "layout must be 0 (three sweeps), 1 (k_stage) or 2 (k_stage_pipe)"; return CFD2D_EINVAL; }
+    if (on == 1) { int rc = build_fused_plan(h); if (rc) return rc; }
+    if (on == 2) { int rc = build_pipe_plan_dev(h); if (rc) return rc; }
+    if (on != 2) ensure_W(h);                 // back to a layout that reads the primitive cache
+    h->fused = on == 1;
+    h->pipe = on == 2;
+    return 0;
+}
+
+int cfd2d_fvm_use_exact_riemann(cfd2d_fvm* h, int on) {
+    if (!h) return CFD2D_EINVAL;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    if (h->comm) cudaStreamSynchronize(h->comm);
+    drop_graph(h);
+    h->exact_riemann = on != 0;
+    if (h->have_plan)
+        for (int st = 1; st <= 2; st++)
+            CUDA_TRY(h, cudaFuncSetAttribute((const void*)stage_kernel(h, st), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->stage_smem));
     return 0;
 }
 
@@ -897,6 +1181,78 @@ int cfd2d_tiling_plan(const cfd2d_mesh* m, int tile_cells, int hilbert, int32_t*
     return 0;
 }
 
+int cfd2d_pipe_plan(const cfd2d_mesh* m, int tile_cells, int dir_bins, int hilbert, int64_t* stats_out) {
+    g_create_error.clear();
+    if (!m || m->nc < 0 || m->nc_ex < m->nc || m->ne < 0) { g_create_error = "bad mesh"; return CFD2D_EINVAL; }
+    std::vector<int> perm, orig;
+    hilbert_cell_order(m->nc, m->nc_ex, m->cell_cx, m->cell_cy, hilbert != 0, perm, orig);
+    HostMesh pm;
+    permute_mesh(m, perm, orig, pm);
+    PipePlan pp;
+    std::string err = build_pipe_plan(pm, tile_cells, dir_bins != 0, pp);
+    if (!err.empty()) { g_create_error = err; return CFD2D_EINVAL; }
+    // ---- invariants k_stage_pipe relies on, re-derived from the blob bytes alone
+    long long owned = 0;
+    for (int t = 0; t < pp.ntiles && err.empty(); t++) {
+        const PipeTile& ti = pp.tiles[t];
+        const unsigned char* b = pp.blob.data() + ((size_t)ti.blob_off << 4);
+        auto gid = [&](int l) { return l < ti.n_own ? ti.cbeg + l : pp.ring[ti.roff + l - ti.n_own]; };
+        if (ti.cbeg != owned || (ti.blob_bytes & 15) || (ti.cbeg & 7)) { err = "tile range / alignment"; break; }
+        owned += ti.n_own;
+        const int S = (ti.n_own + 7) & ~7, R = ti.n_g - ti.n_own;
+        const uint16_t* slot = reinterpret_cast<const uint16_t*>(b + ti.o_slot);
+        const double* en = reinterpret_cast<const double*>(b + ti.o_en);
+        const double* egp = reinterpret_cast<const double*>(b + ti.o_egp);
+        const double* cxy = reinterpret_cast<const double*>(b + ti.o_cxy);
+        const double* Sv = reinterpret_cast<const double*>(b + ti.o_S);
+        for (int l = 0; l < ti.n_l && err.empty(); l++)
+            if (cxy[2 * l] != pm.cell_cx[gid(l)] || cxy[2 * l + 1] != pm.cell_cy[gid(l)]) err = "cell centre";
+        for (int l = 0; l < ti.n_g && err.empty(); l++) {
+            if (Sv[l] != pm.cell_S[gid(l)]) err = "cell area";
+            if (gid(l) >= pm.nc) err = "gradient computed for a non-owned cell";
+        }
+        for (int l = ti.n_g; l < ti.n_l && err.empty(); l++) if (gid(l) < pm.nc) err = "owned ring-1 cell listed as halo";
+        for (int l = 0; l < ti.n_l2 && err.empty(); l++) if (b[ti.o_mat + l] != (unsigned char)pm.cell_mat[gid(l)]) err = "material";
+        for (int j = 0; j < ti.n_own && err.empty(); j++) {
+            const int c = ti.cbeg + j;
+            for (int k = 0; k < 3; k++) {
+                const int es = slot[k * S + j], q = es >> 1, e = pm.cell_edges[3 * (size_t)c + k];
+                if (q >= ti.ne_t) { err = "slot out of the tile's edge range"; break; }
+                double le; uint32_t cl;
+                memcpy(&le, b + ti.o_el + 16 * (size_t)q, 8); memcpy(&cl, b + ti.o_el + 16 * (size_t)q + 8, 4);
+                const int l1 = (int)(cl & 0xffffu), l2 = (int)(cl >> 16);
+                if (le != pm.edge_l[e] || en[2 * q] != pm.edge_nx[e] || en[2 * q + 1] != pm.edge_ny[e]) { err = "slot names the wrong edge (geometry)"; break; }
+                for (int i = 0; i < 4; i++) if (egp[4 * (size_t)q + i] != pm.edge_gp[4 * (size_t)e + i]) err = "Gauss points";
+                if (gid(l1) != pm.edge_c1[e]) { err = "edge c1 local id"; break; }
+                if (pm.edge_c2[e] >= 0 ? (l2 >= ti.n_l || gid(l2) != pm.edge_c2[e]) : (l2 != (0xff00 | pm.edge_bc[e]))) { err = "edge c2 local id / bc"; break; }
+                if (((es & 1) ? pm.edge_c2[e] : pm.edge_c1[e]) != c) { err = "slot side bit"; break; }
+            }
+        }
+        const int* gnb = reinterpret_cast<const int*>(b + ti.o_gnb);
+        const double* gn = reinterpret_cast<const double*>(b + ti.o_gn);
+        for (int r = 0; r < R && err.empty(); r++) {
+            const int c = gid(ti.n_own + r);
+            for (int k = 0; k < 3; k++) {
+                const int e = pm.cell_edges[3 * (size_t)c + k];
+                const bool is1 = pm.edge_c1[e] == c;
+                const int want = is1 ? pm.edge_c2[e] : pm.edge_c1[e];
+                const int nb = gnb[k * R + r];
+                if (want < 0 ? nb != -1 - pm.edge_bc[e] : (nb < 0 || nb >= ti.n_l2 || gid(nb) != want)) { err = "ring-1 gradient neighbour"; break; }
+                if (gn[(k * 3 + 0) * R + r] != (is1 ? pm.edge_nx[e] : -pm.edge_nx[e]) || gn[(k * 3 + 2) * R + r] != pm.edge_l[e]) { err = "ring-1 gradient geometry"; break; }
+            }
+        }
+    }
+    if (err.empty() && owned != pm.nc) err = "tiles do not cover the owned cells";
+    if (!err.empty()) { g_create_error = "pipe plan invariant violated: " + err; return CFD2D_EINVAL; }
+    if (stats_out) {
+        stats_out[0] = pp.ntiles; stats_out[1] = pp.nl2_max; stats_out[2] = pp.ne_max; stats_out[3] = pp.blob_max;
+        stats_out[4] = pp.sum_ne; stats_out[5] = pp.sum_ring1; stats_out[6] = pp.sum_ring2; stats_out[7] = (int64_t)pp.blob.size();
+        stats_out[8] = (int64_t)pp.interior.size(); stats_out[9] = (int64_t)pp.boundary.size();
+        stats_out[10] = pp.nring_max; stats_out[11] = pp.nl_max;
+    }
+    return 0;
+}
+
 int cfd2d_fvm_set_state(cfd2d_fvm* h, const double* ro, const double* ru, const double* rv, const double* re,
                         const uint32_t* flag) {
     if (!h || !ro || !ru || !rv || !re) return CFD2D_EINVAL;
@@ -928,6 +1284,7 @@ int cfd2d_fvm_set_state(cfd2d_fvm* h, const double* ro, const double* ru, const 
 int cfd2d_fvm_calc_time_step(cfd2d_fvm* h, double* tau_out) {
     if (!h) return CFD2D_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    ensure_W(h);
     if (h->ctrl.steady) {
         launch_tau_steady(h);
     } else {
@@ -975,6 +1332,7 @@ int cfd2d_fvm_step_async(cfd2d_fvm* h, int nsteps) {
             cudaError_t e = cudaStreamEndCapture(h->stream, &h->graph);
             h->graph_launches = (int)(h->launches - l0);
             h->launches = l0;
+            if (rc || e != cudaSuccess) { drop_graph(h); cudaGetLastError(); }
             if (rc) return rc;
             CUDA_TRY(h, e);
             CUDA_TRY(h, cudaGraphInstantiate(&h->graph_exec, h->graph, 0));
@@ -997,6 +1355,7 @@ int cfd2d_fvm_sync(cfd2d_fvm* h) {
     if (!h) return CFD2D_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->comm) CUDA_TRY(h, cudaStreamSynchronize(h->comm));
     CUDA_TRY(h, cudaGetLastError());
     return check_device_errors(h);
 }
@@ -1056,14 +1415,12 @@ int64_t cfd2d_fvm_launch_count(const cfd2d_fvm* h) { return h ? h->launches : 0;
 int cfd2d_fvm_calc_grad(cfd2d_fvm* h, double* grad8) {
     if (!h || !grad8) return CFD2D_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
+    ensure_W(h);
     launch_grad(h);
-    double* tmp = nullptr;
-    CUDA_TRY(h, cudaMalloc(&tmp, (size_t)(h->nc ? h->nc : 1) * 64));
-    if (h->nc) k_unpack_grad<<<nblk(2 * (long long)h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->G, tmp);
-    cudaError_t e = cudaMemcpyAsync(grad8, tmp, (size_t)h->nc * 64, cudaMemcpyDeviceToHost, h->stream);
-    cudaStreamSynchronize(h->stream);
-    cudaFree(tmp);
-    CUDA_TRY(h, e);
+    if (!h->grad_tmp) { int rc = dev_alloc(h, &h->grad_tmp, 8 * (size_t)(h->nc ? h->nc : 1)); if (rc) return rc; }
+    if (h->nc) k_unpack_grad<<<nblk(2 * (long long)h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->G, h->grad_tmp);
+    CUDA_TRY(h, cudaMemcpyAsync(grad8, h->grad_tmp, (size_t)h->nc * 64, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
@@ -1072,7 +1429,15 @@ int cfd2d_fvm_edge_fluxes(cfd2d_fvm* h, double* flux4) {
     if (!h || !flux4) return CFD2D_EINVAL;
     CUDA_TRY(h, cudaSetDevice(h->device));
     int rc;
-    if (h->ctrl.order == 2) { launch_grad(h); if ((rc = exchange_G(h, h->stream))) return rc; }
+    ensure_W(h);
+    if (h->ctrl.order == 2) {
+        launch_grad(h);
+        if (h->halo) {                                 // all NCCL traffic of a handle goes through its comm stream
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            if ((rc = exchange_G(h, h->comm))) return rc;
+            CUDA_TRY(h, cudaStreamSynchronize(h->comm));
+        }
+    }
     launch_flux(h, h->Ua, 0);
     std::vector<double> tmp(4 * (size_t)h->ne);
     CUDA_TRY(h, cudaMemcpyAsync(tmp.data(), h->F, (size_t)h->ne * 32, cudaMemcpyDeviceToHost, h->stream));
@@ -1100,7 +1465,17 @@ int cfd2d_fvm_profile(cfd2d_fvm* h, int nsteps, double* ms, int64_t* launches) {
 }
 
 // ---- function-level known-answer entry points ---------------------------------------------------
+static int kat_rim_impl(int device, int n, const double* in8, double gam, int max_newton, int fast, double* out5, int32_t* iters);
+
 int cfd2d_kat_rim_orig(int device, int n, const double* in8, double gam, int max_newton, double* out5, int32_t* iters) {
+    return kat_rim_impl(device, n, in8, gam, max_newton, 0, out5, iters);
+}
+
+int cfd2d_kat_rim_orig_fast(int device, int n, const double* in8, int max_newton, double* out5, int32_t* iters) {
+    return kat_rim_impl(device, n, in8, 1.4, max_newton, 1, out5, iters);   // x^(1/7), x^(5/2): g = 1.4 only (fvm_tvd.cpp:345)
+}
+
+static int kat_rim_impl(int device, int n, const double* in8, double gam, int max_newton, int fast, double* out5, int32_t* iters) {
     g_create_error.clear();
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); g_create_error = "no usable CUDA device"; return CFD2D_ENODEV; }
@@ -1113,7 +1488,7 @@ int cfd2d_kat_rim_orig(int device, int n, const double* in8, double gam, int max
     CUDA_TRY(none, cudaMalloc(&dout, (size_t)n * 40));
     CUDA_TRY(none, cudaMalloc(&dit, (size_t)n * 4));
     CUDA_TRY(none, cudaMemcpy(din, in8, (size_t)n * 64, cudaMemcpyHostToDevice));
-    k_kat_rim<<<nblk(n, 128), 128>>>(make_rim(gam), max_newton, n, din, dout, dit);
+    k_kat_rim<<<nblk(n, 128), 128>>>(make_rim(gam), max_newton, fast, n, din, dout, dit);
     CUDA_TRY(none, cudaDeviceSynchronize());
     CUDA_TRY(none, cudaMemcpy(out5, dout, (size_t)n * 40, cudaMemcpyDeviceToHost));
     std::vector<int> it(n);
@@ -1122,6 +1497,32 @@ int cfd2d_kat_rim_orig(int device, int n, const double* in8, double gam, int max
     int bad = 0;
     for (int i = 0; i < n; i++) { if (iters) iters[i] = it[i]; if (it[i] < 0) bad = CFD2D_ENEWTON; }
     return bad;
+}
+
+int cfd2d_kat_urs(int device, int n, double M, double Cp, int mode, double* io8) {
+    g_create_error.clear();
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); g_create_error = "no usable CUDA device"; return CFD2D_ENODEV; }
+    if (mode < 0 || mode > 2) { g_create_error = "URS mode must be 0, 1 or 2"; return CFD2D_EINVAL; }
+    if (n <= 0) return 0;
+    cfd2d_fvm* none = nullptr;
+    CUDA_TRY(none, cudaSetDevice(device));
+    MatC q;
+    q.M = M;
+    q.Cv = Cp - CFD2D_GR / M;     // global.cpp:11
+    q.gam = Cp / q.Cv;            // global.cpp:12
+    q.gm1 = q.gam - 1;
+    double* d = nullptr;
+    CUDA_TRY(none, cudaMalloc(&d, (size_t)n * 64));
+    cudaError_t e = cudaMemcpy(d, io8, (size_t)n * 64, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        k_kat_urs<<<nblk(n, 128), 128>>>(q, mode, n, d);
+        e = cudaDeviceSynchronize();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(io8, d, (size_t)n * 64, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    CUDA_TRY(none, e);
+    return 0;
 }
 
 int cfd2d_kat_calc_flux(int device, int n, const double* in12, double gam, int flux, double* out4) {

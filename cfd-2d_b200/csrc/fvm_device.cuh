@@ -21,9 +21,16 @@ struct RimC {
     double IAGAM;   // (1/AGAM)            global.cpp:389,395
     double DG1;     // (1+DGAM)            global.cpp:384,391
     double DGGG;    // DGAM*GGAM           global.cpp:384,391
+    double ISGAM;   // 1/SGAM, 1/DG1: reciprocals of the constant divisors, used only by the reduced-instruction
+    double IDG1;    //                solver (fvm_riemann_fast.cuh); the bit-faithful rim_orig_dev divides as written
 };
 
 struct Prim { double r, p, u, v; };
+
+// Material::URS (global.cpp:9-30), the three expressions the path uses
+__device__ __forceinline__ double urs_p(double r, double e, double gm1) { return r * e * gm1; }            // mode 0, :16
+__device__ __forceinline__ double urs_e(double p, double r, double gm1) { return p / (r * gm1); }          // mode 1, :21
+__device__ __forceinline__ double urs_r(double p, double T, double M) { return p * M / (T * CFD2D_GR); }   // mode 2, :26
 
 // FVM_TVD::convertConsToPar (fvm_tvd.cpp:803-813) + Material::URS mode 0 (global.cpp:15-18).
 // Only r,p,u,v are kept: reconstruct/calcFlux read nothing else of an inner state.
@@ -34,13 +41,13 @@ __device__ __forceinline__ Prim cons_to_prim(double ro, double ru, double rv, do
     w.v = rv / ro;
     double E = re / ro;
     double e = E - 0.5 * (w.u * w.u + w.v * w.v);
-    w.p = w.r * e * gm1;
+    w.p = urs_p(w.r, e, gm1);
     return w;
 }
 
 // T as convertConsToPar leaves it: URS(1) after URS(0): e = p/(r*(gam-1)); T = e/Cv (global.cpp:20-23)
 __device__ __forceinline__ double prim_T(const Prim& w, const MatC& m) {
-    double e = w.p / (w.r * m.gm1);
+    double e = urs_e(w.p, w.r, m.gm1);
     return e / m.Cv;
 }
 
@@ -64,9 +71,9 @@ __device__ __forceinline__ Prim ghost_state(const Prim& pL, double TL, int kind,
         double Vy = ny * Un * 2.0;
         pR.u = pL.u - Vx; pR.v = pL.v - Vy; T = TL; pR.p = pL.p;
     }
-    pR.r = pR.p * m.M / (T * CFD2D_GR);               // URS(2), global.cpp:26
+    pR.r = urs_r(pR.p, T, m.M);                       // URS(2), global.cpp:26
     if (E_out) {
-        double e = pR.p / (pR.r * m.gm1);             // URS(1), global.cpp:21
+        double e = urs_e(pR.p, pR.r, m.gm1);          // URS(1), global.cpp:21
         *E_out = e + 0.5 * (pR.u * pR.u + pR.v * pR.v); // fvm_tvd.cpp:703
     }
     return pR;

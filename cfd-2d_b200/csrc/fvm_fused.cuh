@@ -170,6 +170,9 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
                 int it = flux_godunov_dev(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
                 // perimeter edges are evaluated by two tiles: count a Newton-cap hit once per evaluation
                 if (it < 0 && live) atomicAdd(P.err, 1);
+            } else if (FLUX == 2) {
+                int it = flux_godunov_fast(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
+                if (it < 0 && live) atomicAdd(P.err, 1);
             } else {
                 flux_lax_dev(P.rim.GAM, L, EL, R, ER, n.x, n.y, f0, f1, f2, f3);
             }

@@ -10,6 +10,7 @@
 // plus SoA per-slot / per-edge geometry read fully coalesced.
 #pragma once
 #include "fvm_device.cuh"
+#include "fvm_riemann_fast.cuh"
 
 struct KParams {
     int nc, nc_ex, ne, nmat;
@@ -42,7 +43,8 @@ struct KParams {
     unsigned int* flag;
     int* err;               // [0] Newton-cap hits  [1] flagged-cell count  [2] Newton iterations (KAT)
     int* lim_list;          // compacted flagged cells, CALLER ids (unordered until sorted)
-    int lim_cap;                         // power of two >= nc
+    int lim_cap;                         // >= nc
+    unsigned char* rstat;   // [nc_ex] remediation sweep status, all zero between steps
     // cell numbering: the device numbers owned cells along a Hilbert curve (fvm_tiling.h); the
     // caller's numbering only matters for I/O and for the sweep order of remediateLimCells
     const int* c_perm;      // [nc_ex] caller -> device
@@ -77,6 +79,18 @@ __device__ __forceinline__ MatC get_mat(const KParams& P, int c) {
 __global__ void __launch_bounds__(256) k_prim(KParams P, const double4* __restrict__ U, double4* __restrict__ W, int c0, int c1) {
     int c = c0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= c1) return;
+    double4 u = ld4cg(U, c);
+    MatC m = get_mat(P, c);
+    Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
+    st4(W, c, make_double4(w.r, w.p, w.u, w.v));
+}
+
+// the same for a list of cells (multi-rank pipe layout: the cells around the send set)
+__global__ void __launch_bounds__(256) k_prim_list(KParams P, const double4* __restrict__ U, double4* __restrict__ W,
+                                                   const int* __restrict__ list, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = __ldg(list + i);
     double4 u = ld4cg(U, c);
     MatC m = get_mat(P, c);
     Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
@@ -179,7 +193,9 @@ __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const 
 // K3: per-edge linear reconstruction at the two Gauss points + numerical flux
 // (FVM_TVD::reconstruct fvm_tvd.cpp:646-691, calcFlux :602-643, rim_orig global.cpp:232-405, the
 // Gauss-point loop of run() :341-352).  Writes F4[e] = (sum over GPs) * (l*0.5), the quantity the
-// reference scatters (:353-363).  FLUX: 0 Godunov, 1 Lax-Friedrichs.  ORDER: 2 linear, 1 constant.
+// reference scatters (:353-363).  FLUX: 0 Godunov with the bit-faithful rim_orig_dev, 1 Lax-Friedrichs,
+// 2 Godunov with the reduced-instruction solver (fvm_riemann_fast.cuh; the default for Godunov
+// handles).  ORDER: 2 linear, 1 constant.
 //
 // Work decomposition: ONE THREAD PER (edge, Gauss point); the two Gauss points of an edge sit in
 // adjacent lanes.  The exact Riemann solver is a long chain of dependent FP64 divisions/sqrt/exp/log
@@ -197,7 +213,7 @@ template <int FLUX, int ORDER>
 #ifndef CFD2D_FLUXLF_MINB
 #define CFD2D_FLUXLF_MINB 8
 #endif
-__global__ void __launch_bounds__(128, FLUX == 0 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
+__global__ void __launch_bounds__(128, FLUX != 1 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
 k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
        const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2, int e0, int e1) {
     // edges [e0, e1) of the device edge order (multi-rank handles: interior edges first, edges that
@@ -247,6 +263,9 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
     double f0, f1, f2, f3;
     if (FLUX == 0) {
         int it = flux_godunov_dev(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
+        if (it < 0 && live) atomicAdd(P.err, 1);
+    } else if (FLUX == 2) {
+        int it = flux_godunov_fast(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
         if (it < 0 && live) atomicAdd(P.err, 1);
     } else {
         flux_lax_dev(P.rim.GAM, L, EL, R, ER, n.x, n.y, f0, f1, f2, f3);
@@ -401,48 +420,72 @@ __global__ void __launch_bounds__(256, CFD2D_LF1_MINB) k_cell_lf1(KParams P, con
 }
 
 // ---------------------------------------------------------------------------------------------
-// K6: FVM_TVD::remediateLimCells (fvm_tvd.cpp:464-499).  Rare path.  One block: sort the flagged
-// list ascending by caller id (bitonic, in global memory), then thread 0 replays the reference's in-place,
-// ascending-cell-order sweep (the order matters when two flagged cells are neighbours).  Keeps the
-// reference's quirk: only edges[].c2 is averaged, i.e. the cell itself when it is the edge's c2.
+// K6: FVM_TVD::remediateLimCells (fvm_tvd.cpp:464-499).  Rare path (returns at once when nothing is
+// flagged).  The reference sweeps the cells in ascending id and overwrites in place, so a flagged
+// cell c sees, for a flagged neighbour j = edges[].c2,
+//     the REMEDIATED value of j when j < c  (already swept),
+//     the ORIGINAL   value of j when j > c  (not reached yet), and its own original value when the
+// cell itself is the edge's c2 (the reference's self-neighbour quirk, kept).
+// That is a dependency DAG, not a serial chain: the flagged cells are snapshotted (Uold), then swept
+// as a wavefront by one CTA -- every round computes all pending cells whose lower-numbered flagged
+// c2-neighbours are done (reading new values of those, snapshot values of higher-numbered flagged
+// ones) and commits them after a barrier.  Meshes from the reference's readers always have c1 < c2
+// (an edge is created by its lower-numbered cell, MeshReaderSalomeUnv.cpp:119-217), so there the
+// whole sweep is ONE round; chains only arise for caller meshes with other edge orientations.
+// Ids are the CALLER's (the reference's sweep order), the sums run in Cell::edgesInd slot order.
+// Halo cells (multi-rank) are read as delivered by the state exchange before this kernel: they are
+// the owner's pre-remediation values, which is what the serial sweep reads because a halo cell
+// that is an edge's c2 has the higher global id (checked at create() when cell_gid is given).
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_remediate(KParams P, double4* U, double4* W) {
+__global__ void __launch_bounds__(1024) k_remediate(KParams P, double4* U, double4* Uold, double4* W, double4* Unew) {
     int n = P.err[1];
     if (n == 0) return;
     if (n > P.lim_cap) n = P.lim_cap;
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    int* a = P.lim_list;
-    for (int i = n + threadIdx.x; i < np2; i += blockDim.x) a[i] = 0x7fffffff;
-    __syncthreads();
-    for (int k = 2; k <= np2; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-                int ixj = i ^ j;
-                if (ixj > i) {
-                    int x = a[i], y = a[ixj];
-                    bool up = (i & k) == 0;
-                    if ((x > y) == up) { a[i] = y; a[ixj] = x; }
-                }
-            }
-            __syncthreads();
-        }
+    const int* a = P.lim_list;                           // caller ids, any order
+    unsigned char* rs = P.rstat;                         // 0 not flagged, 1 pending, 3 computed this round, 2 done
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        int c = P.c_perm[a[q]];
+        Uold[c] = U[c];
+        rs[c] = 1;
     }
-    if (threadIdx.x == 0) {
-        for (int q = 0; q < n; q++) {
-            int c = P.c_perm[a[q]];          // ascending CALLER id = the reference's sweep order
-            double sRO = 0.0, sRU = 0.0, sRV = 0.0, sRE = 0.0, S = 0.0;
+    __syncthreads();
+    for (;;) {
+        int pending = 0;
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {
+            const int idc = a[q];
+            const int c = P.c_perm[idc];
+            if (rs[c] != 1) continue;
+            int js[3];
+            bool ready = true;
+#pragma unroll
             for (int k = 0; k < 3; k++) {
                 int es = P.s_es[(size_t)k * P.nc + c];
                 int j = P.e_c[es >> 1].y;
+                js[k] = j;
+                if (j >= 0 && j != c && j < P.nc && (rs[j] & 1) && P.c_orig[j] < idc) ready = false;
+            }
+            if (!ready) { pending = 1; continue; }
+            double sRO = 0.0, sRU = 0.0, sRV = 0.0, sRE = 0.0, S = 0.0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                int j = js[k];
                 if (j >= 0) {
                     double s = P.cell_S[j];
-                    double4 u = U[j];
+                    // a flagged neighbour the serial sweep has not reached yet: its original value
+                    bool later = j != c && j < P.nc && rs[j] != 0 && P.c_orig[j] > idc;
+                    double4 u = later ? Uold[j] : U[j];
                     S += s;
                     sRO += u.x * s; sRU += u.y * s; sRV += u.z * s; sRE += u.w * s;
                 }
             }
-            double4 u = make_double4(sRO / S, sRU / S, sRV / S, sRE / S);
+            Unew[q] = make_double4(sRO / S, sRU / S, sRV / S, sRE / S);
+            rs[c] = 3;
+        }
+        __syncthreads();
+        for (int q = threadIdx.x; q < n; q += blockDim.x) {
+            const int c = P.c_perm[a[q]];
+            if (rs[c] != 3) continue;
+            double4 u = Unew[q];
             U[c] = u;
             MatC m = get_mat(P, c);
             Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
@@ -451,9 +494,12 @@ __global__ void __launch_bounds__(1024) k_remediate(KParams P, double4* U, doubl
             fl += 0x010000u;
             if (fl & 0x200000u) fl &= 0x001110u;
             P.flag[c] = fl;
+            rs[c] = 2;
         }
-        P.err[1] = 0;
+        if (!__syncthreads_or(pending)) break;
     }
+    for (int q = threadIdx.x; q < n; q += blockDim.x) rs[P.c_perm[a[q]]] = 0;
+    if (threadIdx.x == 0) P.err[1] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -519,15 +565,41 @@ __global__ void __launch_bounds__(256) k_unpack_grad(int n, const int* __restric
 // ---------------------------------------------------------------------------------------------
 // function-level known-answer kernels
 // ---------------------------------------------------------------------------------------------
-__global__ void k_kat_rim(RimC rc, int max_newton, int n, const double* __restrict__ in8, double* __restrict__ out5, int* __restrict__ iters) {
+__global__ void k_kat_rim(RimC rc, int max_newton, int fast, int n, const double* __restrict__ in8, double* __restrict__ out5, int* __restrict__ iters) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double* a = in8 + 8 * (size_t)i;
     double RI, EI, PI, UI, VI;
-    int it = rim_orig_dev(rc, max_newton, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], RI, EI, PI, UI, VI);
+    int it = fast ? rim_orig_fast(rc, max_newton, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], RI, EI, PI, UI, VI)
+                  : rim_orig_dev(rc, max_newton, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], RI, EI, PI, UI, VI);
     double* q = out5 + 5 * (size_t)i;
     q[0] = RI; q[1] = EI; q[2] = PI; q[3] = UI; q[4] = VI;
     if (iters) iters[i] = it;
+}
+
+// Material::URS (global.cpp:9-30) as the kernels evaluate it: mode 0 is the p / cz part of
+// cons_to_prim + prim_cz, mode 1 is prim_T, mode 2 the ghost density of ghost_state.
+// io8[n][8] = r,p,e,E,u,v,cz,T in place, like the reference's Param.
+__global__ void k_kat_urs(MatC m, int mode, int n, double* __restrict__ io8) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* a = io8 + 8 * (size_t)i;
+    if (mode == 0) {
+        // cons_to_prim forms e = E - 0.5*(u*u+v*v) itself; feed it conservative variables that give back this e
+        Prim w; w.r = a[0]; w.u = 0.0; w.v = 0.0;
+        w.p = urs_p(a[0], a[2], m.gm1);
+        a[1] = w.p;
+        a[6] = prim_cz(w, m);
+    } else if (mode == 1) {
+        Prim w; w.r = a[0]; w.p = a[1]; w.u = 0.0; w.v = 0.0;
+        a[2] = urs_e(a[1], a[0], m.gm1);
+        a[7] = prim_T(w, m);
+    } else {
+        Prim w; w.p = a[1]; w.u = 0.0; w.v = 0.0;
+        w.r = urs_r(a[1], a[7], m.M);
+        a[0] = w.r;
+        a[6] = prim_cz(w, m);
+    }
 }
 
 __global__ void k_kat_flux(RimC rc, int flux, int n, const double* __restrict__ in12, double* __restrict__ out4) {
@@ -537,6 +609,7 @@ __global__ void k_kat_flux(RimC rc, int flux, int n, const double* __restrict__ 
     Prim L = {a[0], a[1], a[2], a[3]}, R = {a[5], a[6], a[7], a[8]};
     double f0, f1, f2, f3;
     if (flux == 1) flux_lax_dev(rc.GAM, L, a[4], R, a[9], a[10], a[11], f0, f1, f2, f3);
+    else if (flux == 2) flux_godunov_fast(rc, 1000, L, R, a[10], a[11], f0, f1, f2, f3);
     else flux_godunov_dev(rc, 1000, L, R, a[10], a[11], f0, f1, f2, f3);
     double* q = out4 + 4 * (size_t)i;
     q[0] = f0; q[1] = f1; q[2] = f2; q[3] = f3;

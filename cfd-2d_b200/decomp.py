@@ -98,7 +98,7 @@ class RankMesh:
     def halo_dict(self, nccl_unique_id: bytes):
         flat = np.concatenate([np.asarray(s, dtype=np.int32) for s in self.send_ind]) if self.nranks else np.empty(0, np.int32)
         return dict(rank=self.rank, nranks=self.nranks, recv_count=self.recv_count, send_count=self.send_count,
-                    send_ind=flat, nccl_unique_id=nccl_unique_id)
+                    send_ind=flat, nccl_unique_id=nccl_unique_id, cell_gid=self.g_cells)
 
 
 def decompose(m: _mesh.Mesh, part: np.ndarray, nranks: int, only_rank: int | None = None) -> list[RankMesh]:

@@ -48,7 +48,7 @@ class CCtrl(C.Structure):
 
 class CHalo(C.Structure):
     _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("recv_count", _ip), ("send_count", _ip),
-                ("send_ind", _ip), ("nccl_unique_id", C.c_void_p)]
+                ("send_ind", _ip), ("nccl_unique_id", C.c_void_p), ("cell_gid", _ip)]
 
 
 class CFDError(RuntimeError):
@@ -132,6 +132,9 @@ def load_library() -> C.CDLL:
     lib.cfd2d_fvm_edge_fluxes.argtypes = [H, _dp]
     lib.cfd2d_kat_rim_orig.argtypes = [C.c_int, C.c_int, _dp, C.c_double, C.c_int, _dp, _ip]
     lib.cfd2d_kat_calc_flux.argtypes = [C.c_int, C.c_int, _dp, C.c_double, C.c_int, _dp]
+    lib.cfd2d_kat_rim_orig_fast.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]
+    lib.cfd2d_fvm_use_exact_riemann.argtypes = [H, C.c_int]
+    lib.cfd2d_kat_urs.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp]
     lib.cfd2d_fvm_profile.argtypes = [H, C.c_int, _dp, C.POINTER(C.c_int64)]
     lib.cfd2d_fvm_launch_count.argtypes = [H]
     lib.cfd2d_fvm_launch_count.restype = C.c_int64
@@ -141,6 +144,7 @@ def load_library() -> C.CDLL:
     lib.cfd2d_fvm_plan_summary.argtypes = [H]
     lib.cfd2d_fvm_plan_summary.restype = C.c_char_p
     lib.cfd2d_tiling_plan.argtypes = [C.POINTER(CMesh), C.c_int, C.c_int, _ip, C.POINTER(C.c_int64)]
+    lib.cfd2d_pipe_plan.argtypes = [C.POINTER(CMesh), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]
     lib.cfd2d_fvm_last_error.argtypes = [H]
     lib.cfd2d_fvm_last_error.restype = C.c_char_p
     lib.cfd2d_version.restype = C.c_char_p
@@ -151,9 +155,10 @@ def load_library() -> C.CDLL:
 EXPORTS = [
     "cfd2d_fvm_create", "cfd2d_fvm_destroy", "cfd2d_fvm_set_state", "cfd2d_fvm_calc_time_step", "cfd2d_fvm_step",
     "cfd2d_fvm_step_async", "cfd2d_fvm_sync", "cfd2d_fvm_get_state", "cfd2d_fvm_get_primitive", "cfd2d_fvm_tau",
-    "cfd2d_fvm_time", "cfd2d_fvm_calc_grad", "cfd2d_fvm_edge_fluxes", "cfd2d_kat_rim_orig", "cfd2d_kat_calc_flux",
+    "cfd2d_fvm_time", "cfd2d_fvm_calc_grad", "cfd2d_fvm_edge_fluxes", "cfd2d_kat_rim_orig", "cfd2d_kat_calc_flux", "cfd2d_kat_urs",
+    "cfd2d_kat_rim_orig_fast", "cfd2d_fvm_use_exact_riemann",
     "cfd2d_fvm_profile", "cfd2d_fvm_launch_count", "cfd2d_fvm_set_stream", "cfd2d_fvm_use_graph",
-    "cfd2d_fvm_use_fused", "cfd2d_fvm_plan_summary", "cfd2d_tiling_plan",
+    "cfd2d_fvm_use_fused", "cfd2d_fvm_plan_summary", "cfd2d_tiling_plan", "cfd2d_pipe_plan",
     "cfd2d_unv_read", "cfd2d_unv_counts", "cfd2d_unv_copy", "cfd2d_unv_group_name", "cfd2d_unv_group_counts",
     "cfd2d_unv_group_copy", "cfd2d_unv_free",
     "cfd2d_fvm_last_error", "cfd2d_version",
@@ -174,11 +179,15 @@ class Solver:
             self._halo_arrays = dict(recv_count=_i32(halo["recv_count"]), send_count=_i32(halo["send_count"]),
                                      send_ind=_i32(halo["send_ind"] if len(halo["send_ind"]) else [0]))
             self._nccl_id = C.create_string_buffer(bytes(halo["nccl_unique_id"]), 128)
+            gid = halo.get("cell_gid")
+            if gid is not None:
+                self._halo_arrays["cell_gid"] = _i32(gid)
             self._halo = CHalo(int(halo["rank"]), int(halo["nranks"]),
                                self._halo_arrays["recv_count"].ctypes.data_as(_ip),
                                self._halo_arrays["send_count"].ctypes.data_as(_ip),
                                self._halo_arrays["send_ind"].ctypes.data_as(_ip),
-                               C.cast(self._nccl_id, C.c_void_p))
+                               C.cast(self._nccl_id, C.c_void_p),
+                               self._halo_arrays["cell_gid"].ctypes.data_as(_ip) if gid is not None else None)
             halo_ref = C.byref(self._halo)
         rc = self.lib.cfd2d_fvm_create(C.byref(self.pk.mesh), C.byref(self.pk.phys), C.byref(self.pk.ctrl),
                                        halo_ref, int(device), C.byref(self.h))
@@ -274,9 +283,15 @@ class Solver:
     def use_graph(self, on: bool):
         self._chk(self.lib.cfd2d_fvm_use_graph(self.h, 1 if on else 0))
 
-    def use_fused(self, on: bool):
-        """True: one tile-fused kernel per RK stage; False (default): three sweeps per stage."""
-        self._chk(self.lib.cfd2d_fvm_use_fused(self.h, 1 if on else 0))
+    def use_fused(self, on):
+        """Step layout: 0 / False = three sweeps per stage, 1 / True = one tile-fused kernel per RK stage
+        (k_stage), 2 = the persistent, bulk-copy-fed tile kernel (k_stage_pipe).  All give the same bits."""
+        self._chk(self.lib.cfd2d_fvm_use_fused(self.h, int(on)))
+
+    def use_exact_riemann(self, on: bool):
+        """Godunov handles: True = rim_orig evaluated in the reference's operation order (rim_orig_dev),
+        False (default) = the reduced-instruction solver (csrc/fvm_riemann_fast.cuh)."""
+        self._chk(self.lib.cfd2d_fvm_use_exact_riemann(self.h, 1 if on else 0))
 
     @property
     def plan_summary(self) -> str:
@@ -309,13 +324,35 @@ def tiling_plan(m, t: _task.Task, tile_cells=512, hilbert=True, nc_owned=None):
     return perm, dict(zip(keys, (int(x) for x in stats)))
 
 
-def kat_rim_orig(in8, gam=1.4, max_newton=0, device=0):
+def pipe_plan(m, t: _task.Task, tile_cells=128, dir_bins=True, hilbert=True, nc_owned=None):
+    """Host-only: statistics of the per-tile blobs of the pipelined tile kernel (layout 2); every table
+    is re-derived from the blob bytes inside the hook (CPU test hook)."""
+    lib = load_library()
+    pk = Packed(m, t, nc_owned=nc_owned)
+    stats = np.zeros(12, np.int64)
+    rc = lib.cfd2d_pipe_plan(C.byref(pk.mesh), int(tile_cells), 1 if dir_bins else 0, 1 if hilbert else 0,
+                             stats.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc != 0:
+        msg = lib.cfd2d_fvm_last_error(None)
+        raise CFDError(rc, msg.decode() if msg else "")
+    keys = ("ntiles", "nl2_max", "ne_max", "blob_max", "sum_ne", "sum_ring1", "sum_ring2", "blob_bytes", "interior", "boundary",
+            "nring_max", "nl_max")
+    return dict(zip(keys, (int(x) for x in stats)))
+
+
+def kat_rim_orig(in8, gam=1.4, max_newton=0, device=0, fast=False):
+    """rim_orig on the device: fast=False the statement that keeps the reference's operation order,
+    fast=True the reduced-instruction solver the Godunov kernels use by default (g = 1.4 only)."""
     lib = load_library()
     a = _f64(in8)
     out = np.empty((a.shape[0], 5))
     it = np.empty(a.shape[0], np.int32)
-    rc = lib.cfd2d_kat_rim_orig(device, a.shape[0], a.ctypes.data_as(_dp), float(gam), int(max_newton),
-                                out.ctypes.data_as(_dp), it.ctypes.data_as(_ip))
+    if fast:
+        rc = lib.cfd2d_kat_rim_orig_fast(device, a.shape[0], a.ctypes.data_as(_dp), int(max_newton),
+                                         out.ctypes.data_as(_dp), it.ctypes.data_as(_ip))
+    else:
+        rc = lib.cfd2d_kat_rim_orig(device, a.shape[0], a.ctypes.data_as(_dp), float(gam), int(max_newton),
+                                    out.ctypes.data_as(_dp), it.ctypes.data_as(_ip))
     if rc not in (0, -4):
         raise CFDError(rc, "kat_rim_orig")
     return out, it
@@ -329,6 +366,16 @@ def kat_calc_flux(in12, gam=1.4, flux=FLUX_GODUNOV, device=0):
     if rc != 0:
         raise CFDError(rc, "kat_calc_flux")
     return out
+
+
+def kat_urs(io8, M, Cp, mode, device=0):
+    """Material::URS (global.cpp:9-30) on the device; io8[n][8] = r,p,e,E,u,v,cz,T (a copy is returned)."""
+    lib = load_library()
+    a = np.array(io8, dtype=np.float64, copy=True, order="C")
+    rc = lib.cfd2d_kat_urs(device, a.shape[0], float(M), float(Cp), int(mode), a.ctypes.data_as(_dp))
+    if rc != 0:
+        raise CFDError(rc, "kat_urs")
+    return a
 
 
 # ------------------------------------------------------------------------------------------------

@@ -101,6 +101,11 @@ typedef struct cfd2d_halo {
     const int32_t* send_count;  /* [nranks] sendInd[p].size()                                      */
     const int32_t* send_ind;    /* [sum send_count] owned-cell indices, rank-major (Grid::sendInd) */
     const void*    nccl_unique_id; /* 128-byte ncclUniqueId, identical on every rank               */
+    const int32_t* cell_gid;    /* [nc_ex] optional (may be NULL): global id of every local cell   */
+                                /* (Decomp's cell map, decomp.cpp:165-211).  Used to verify that   */
+                                /* every edge across the partition keeps id(c1) < id(c2), which    */
+                                /* makes the per-rank remediateLimCells equal the serial ascending  */
+                                /* sweep (fvm_tvd.cpp:464-499)                                      */
 } cfd2d_halo;
 
 typedef struct cfd2d_fvm cfd2d_fvm;
@@ -157,8 +162,19 @@ int cfd2d_fvm_edge_fluxes(cfd2d_fvm* h, double* flux4);
  *   RI,EI,PI,UI,VI; iters[n] (may be NULL) = Newton iterations taken.                             */
 int cfd2d_kat_rim_orig(int device, int n, const double* in8, double gam, int max_newton,
                        double* out5, int32_t* iters);
-/*   FVM_TVD::calcFlux (fvm_tvd.cpp:602-643): in12[n][12] = rL,pL,uL,vL,EL, rR,pR,uR,vR,ER, nx,ny  */
+/*   the same through the reduced-instruction solver the Godunov kernels use by default
+ *   (cfd2d_fvm_use_exact_riemann); gamma is the flux loop's hard-coded 1.4 (fvm_tvd.cpp:345).     */
+int cfd2d_kat_rim_orig_fast(int device, int n, const double* in8, int max_newton, double* out5,
+                            int32_t* iters);
+/*   FVM_TVD::calcFlux (fvm_tvd.cpp:602-643): in12[n][12] = rL,pL,uL,vL,EL, rR,pR,uR,vR,ER, nx,ny;
+ *   flux = CFD2D_FLUX_GODUNOV (bit-faithful rim_orig), CFD2D_FLUX_LAX, or 2 = Godunov through the
+ *   reduced-instruction solver.                                                                    */
 int cfd2d_kat_calc_flux(int device, int n, const double* in12, double gam, int flux, double* out4);
+
+/*   Material::URS (global.cpp:9-30): io8[n][8] = r,p,e,E,u,v,cz,T updated in place; mode 0: (r,e) ->
+ *   p,cz; mode 1: (r,p) -> e,T; mode 2: (p,T) -> r,cz -- the three uses on this path
+ *   (convertConsToPar fvm_tvd.cpp:803-813, boundaryCond :694-711).                                 */
+int cfd2d_kat_urs(int device, int n, double M, double Cp, int mode, double* io8);
 
 /* Per-kernel device time: runs nsteps steps with CUDA events around every launch.
  * ms[CFD2D_NKERNELS] receives the summed milliseconds per kernel, launches[] the launch counts.   */
@@ -184,11 +200,19 @@ int cfd2d_fvm_set_stream(cfd2d_fvm* h, void* cuda_stream);
 /* Enable/disable CUDA-graph replay of the step (default on).                                      */
 int cfd2d_fvm_use_graph(cfd2d_fvm* h, int on);
 
-/* Choose how the step is laid out on the device: 0 (default) = three sweeps per stage as in
- * FVM_TVD::run (gradient, edge-flux and update kernels with HBM staging), 1 = one tile-fused
- * kernel per RK stage (gradients and edge fluxes stay in shared memory; fewer HBM bytes, more
- * exposed latency -- see profiles/README.md).  Both produce the same bits.                        */
+/* Choose how the step is laid out on the device: 0 = three sweeps per stage as in FVM_TVD::run
+ * (gradient, edge-flux and update kernels with HBM staging); 1 = one tile-fused kernel per RK stage
+ * (k_stage: gradients and edge fluxes stay in shared memory); 2 = the persistent, software-pipelined
+ * tile kernel (k_stage_pipe: per-tile tables and state ranges arrive by cp.async.bulk + mbarrier one
+ * tile ahead, the primitive cache leaves HBM).  All three produce the same bits.  CFD2D_FUSED=0|1|2
+ * selects the layout at create().                                                                  */
 int cfd2d_fvm_use_fused(cfd2d_fvm* h, int on);
+
+/* Godunov handles only.  0 (default): rim_orig (global.cpp:232-405) is evaluated by the reduced-
+ * instruction solver (shared reciprocals, FMA, x^(1/7) by Newton; same algorithm, same branches,
+ * results within a few ulp per operation -- inside the 1e-12 contract of this exp/log path);
+ * 1: by the statement that keeps the reference's operation order (CFD2D_EXACT_RIEMANN=1 at create).  */
+int cfd2d_fvm_use_exact_riemann(cfd2d_fvm* h, int on);
 
 /* One-line description of the tile plan of this handle (tiles, ring overhead, shared memory).     */
 const char* cfd2d_fvm_plan_summary(const cfd2d_fvm* h);
@@ -200,6 +224,13 @@ const char* cfd2d_fvm_plan_summary(const cfd2d_fvm* h);
  * interior tiles, boundary tiles.  Returns 0 or CFD2D_EINVAL (message via last_error(NULL)).      */
 int cfd2d_tiling_plan(const cfd2d_mesh* mesh, int tile_cells, int hilbert, int32_t* perm_out,
                       int64_t* stats_out);
+
+/* Host-only test hook for the plan of the pipelined tile kernel (layout 2): builds the per-tile blobs
+ * create() would build and re-derives every table from the blob bytes (slots -> edges -> local cell
+ * ids, geometry, ring-1 gradient tables, materials).  stats_out[12] (may be NULL) = ntiles, max
+ * staged cells, max edges, max blob bytes, sum edges, sum ring 1, sum ring 2, blob bytes, interior
+ * tiles, boundary tiles, max gathered records, max cells with a gradient.                          */
+int cfd2d_pipe_plan(const cfd2d_mesh* mesh, int tile_cells, int dir_bins, int hilbert, int64_t* stats_out);
 
 /* Multi-rank bootstrap: a 128-byte ncclUniqueId created on one rank (ncclGetUniqueId); the caller
  * ships it to the other ranks (MPI_Bcast in the reference host, torch.distributed here) and every

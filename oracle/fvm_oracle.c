@@ -117,6 +117,19 @@ static void urs(const fvm_oracle* o, int imat, Param* par, int mode) {
     }
 }
 
+/* known-answer hook: Material::URS on io8[n][8] = r,p,e,E,u,v,cz,T in place */
+void fvm_oracle_urs(int n, double M, double Cp, int mode, double* io8) {
+    fvm_oracle o;
+    memset(&o, 0, sizeof o);
+    o.mM = &M; o.mCp = &Cp;
+    for (int i = 0; i < n; i++) {
+        double* a = io8 + 8 * (size_t)i;
+        Param p = { a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7] };
+        urs(&o, 0, &p, mode);
+        a[0] = p.r; a[1] = p.p; a[2] = p.e; a[3] = p.E; a[4] = p.u; a[5] = p.v; a[6] = p.cz; a[7] = p.T;
+    }
+}
+
 /* FVM_TVD::convertConsToPar, fvm_tvd.cpp:803-813 */
 static void prim(const fvm_oracle* o, int c, Param* par) {
     par->r = o->ro[c];

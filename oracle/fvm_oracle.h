@@ -22,6 +22,7 @@ void   fvm_oracle_get_primitive(fvm_oracle* o, double* r, double* p, double* T, 
 long long fvm_oracle_newton_iters(const fvm_oracle* o);       /* total Newton iterations so far */
 long long fvm_oracle_riemann_calls(const fvm_oracle* o);
 int    fvm_oracle_rim_orig(int n, const double* in8, double gam, int max_newton, double* out5, int32_t* iters);
+void   fvm_oracle_urs(int n, double M, double Cp, int mode, double* io8);   /* Material::URS, in place */
 void   fvm_oracle_calc_flux(int n, const double* in12, double gam, int flux, double* out4);
 #ifdef __cplusplus
 }

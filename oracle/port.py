@@ -51,6 +51,7 @@ def load():
     lib.fvm_oracle_riemann_calls.restype = C.c_longlong
     lib.fvm_oracle_rim_orig.argtypes = [C.c_int, _dp, C.c_double, C.c_int, _dp, _ip]
     lib.fvm_oracle_calc_flux.argtypes = [C.c_int, _dp, C.c_double, C.c_int, _dp]
+    lib.fvm_oracle_urs.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, _dp]
     _lib = lib
     return lib
 
@@ -126,3 +127,9 @@ def calc_flux(in12, gam=1.4, flux=0):
     out = np.empty((a.shape[0], 4))
     load().fvm_oracle_calc_flux(a.shape[0], a.ctypes.data_as(_dp), float(gam), int(flux), out.ctypes.data_as(_dp))
     return out
+
+
+def urs(io8, M, Cp, mode):
+    a = np.array(io8, dtype=np.float64, copy=True, order="C")
+    load().fvm_oracle_urs(a.shape[0], float(M), float(Cp), int(mode), a.ctypes.data_as(_dp))
+    return a

@@ -25,11 +25,18 @@ def main():
     # stream (default), the same serialised on one stream, and the tile-fused stage kernel
     modes = {"overlap": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1"}, "serial": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "0"},
              "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1"}}
-    cases_ = (("metis", 0, 2, 0), ("slab", 1, 2, 0), ("metis", 1, 1, 0), ("slab", 0, 2, 1))
-    for mode, partition, flux, order, steady in [(m,) + c for m in modes for c in cases_]:
+    # (partition, flux, order, steady, p_max): the last two cases lower the pressure limit below the
+    # initial peak so that a blob of adjacent cells trips the limiter ACROSS the partition cut:
+    # remediateLimCells (fvm_tvd.cpp:464-499) then rewrites send cells after the end-of-step exchange
+    # and reads flagged halo neighbours -- the per-rank sweep must still equal the serial one
+    cases_ = (("metis", 0, 2, 0, None), ("slab", 1, 2, 0, None), ("metis", 1, 1, 0, None), ("slab", 0, 2, 1, None),
+              ("slab", 1, 2, 0, 1.005e5), ("metis", 0, 2, 0, 1.005e5))
+    for mode, partition, flux, order, steady, p_max in [(m,) + c for m in modes for c in cases_]:
         os.environ.update(modes[mode])
         c = cases.channel(96, 48, jitter=0.2, shuffle=True)
         c.task.steady = steady
+        if p_max is not None:
+            c.task.p_max = p_max
         st = c.smooth_state()
         if partition == "metis" and not os.path.exists(decomp.METIS_LIB):
             partition = "slab"
@@ -40,6 +47,9 @@ def main():
         s.step(12)
         got = s.get_state()
         rm = s.rank_mesh
+        nflag = torch.zeros(world, dtype=torch.int64, device="cuda")
+        nflag[rank] = int((got[5] != 0).sum())           # cells the limiter touched on this rank
+        dist.all_reduce(nflag)
         # assemble the global state on every rank
         glob = [torch.zeros(nc_tot, dtype=torch.float64, device="cuda") for _ in range(4)]
         idx = torch.from_numpy(rm.g_cells[:rm.nc].astype(np.int64)).cuda()
@@ -56,8 +66,23 @@ def main():
             ref = s1.get_state()
             s1.close()
             same = all(np.array_equal(glob[k].cpu().numpy(), ref[k]) for k in range(4)) and tau == tau1
-            print(f"[multi-gpu x{world}] mode={mode} partition={partition} flux={flux} order={order} steady={steady}: "
-                  f"bitwise equal to 1 GPU = {same}, tau={tau}", flush=True)
+            extra = ""
+            if p_max is not None:
+                # the limiter must really have tripped on both sides of a cut, and the run must still be
+                # the reference's: C oracle (serial ascending sweep), LF bit-exact / Godunov <= 1e-12
+                from oracle import port
+                import parity_cases as pc
+                ranks_hit = int((nflag > 0).sum().item())
+                o = port.OracleSolver(c.mesh, c.task, flux, order)
+                o.set_state(*st); o.calc_time_step(); o.step(12)
+                oref = o.get_state(); o.close()
+                err = max(pc.err_norm(ref[:4], oref[:4]))
+                flags_ok = bool(np.array_equal(ref[5], oref[5]))
+                good = ranks_hit >= 2 and flags_ok and (err == 0.0 if flux == 1 else err < 1e-12)
+                extra = f" limiter: touched cells per rank={nflag.tolist()} err_vs_oracle={err:.2e} flags_equal={flags_ok} ok={good}"
+                same = same and good
+            print(f"[multi-gpu x{world}] mode={mode} partition={partition} flux={flux} order={order} steady={steady} p_max={p_max}: "
+                  f"bitwise equal to 1 GPU = {same}, tau={tau}{extra}", flush=True)
             ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)

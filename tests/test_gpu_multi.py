@@ -1,4 +1,6 @@
-"""GPU (-m gpu): multi-GPU path (needs >= 2 GPUs, otherwise skipped): METIS / slab partition, owned/halo
+"""GPU (-m gpu): multi-GPU path.  NEEDS >= 2 GPUs -- NCCL refuses two ranks on one device, so on a
+1-GPU box these tests are skipped and that skip is expected (the builder's 2/4/8-GPU logs of exactly
+this file are committed under profiles/). METIS / slab partition, owned/halo
 renumbering, NCCL send/recv halo exchange -- the assembled state must equal the single-GPU state
 bit for bit (same kernels, same per-cell summation order, global edge orientation on every rank)."""
 import os
@@ -27,4 +29,4 @@ def test_multi_gpu_equals_single_gpu_bitwise(n):
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0
-    assert r.stdout.count("bitwise equal to 1 GPU = True") == 12      # 3 step layouts x 4 cases
+    assert r.stdout.count("bitwise equal to 1 GPU = True") == 18      # 3 step layouts x 6 cases (2 trip the limiter across a cut)

@@ -30,22 +30,46 @@ def relerr(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
-def test_kat_rim_orig_vs_oracle_and_golden():
+@pytest.mark.parametrize("fast", [False, True])
+def test_kat_rim_orig_vs_oracle_and_golden(fast):
+    """fast=False: rim_orig_dev (the reference's operation order); fast=True: the reduced-instruction
+    solver the Godunov kernels use by default (csrc/fvm_riemann_fast.cuh)."""
     a = pc.kat_rim_inputs()
-    got, it = fvm.kat_rim_orig(a)
+    got, it = fvm.kat_rim_orig(a, fast=fast)
     ref, rit = P.rim_orig(a)
     g = gold("kat_rim_orig")["out"]
     assert np.array_equal(ref, g)
     assert (it >= 0).all()
     # Newton trip counts agree except where a last-bit exp/log difference flips the exit test
-    assert (it != rit).mean() < 1e-2
+    # |residual| > 1e-5 (global.cpp:307): there the two sides stop one iteration apart, both inside the
+    # reference's own tolerance.  Observed rate is printed; those rows are bounded separately.
     same = it == rit
+    rate = float((~same).mean())
+    print(f"rim_orig KAT: {int((~same).sum())} of {len(it)} inputs differ in Newton trip count (rate {rate:.2e})")
+    assert rate < 2.5e-3, rate
     scale = np.abs(g).max(axis=0)
     err = (np.abs(got - g)[same] / scale).max()
     assert err < 1e-13, err
+    if (~same).any():
+        # one Newton step from a residual <= ~1e-5 m/s moves P by <= res*rho*c/2 ~ 1e-2 Pa of ~1e5
+        assert np.abs(it - rit)[~same].max() == 1
+        err2 = (np.abs(got - g)[~same] / scale).max()
+        print(f"rim_orig KAT: max scaled error on those rows {err2:.2e}")
+        assert err2 < 1e-6, err2
     # the vacuum branch and the pure-left/right sampling never touch exp/log: bit-exact there
     vac = rit == 0
-    assert vac.sum() >= 50 and np.array_equal(got[vac], g[vac])
+    assert vac.sum() >= 50
+    if not fast:
+        assert np.array_equal(got[vac], g[vac])
+
+
+def test_kat_urs_bit_exact():
+    """Material::URS modes 0/1/2 (global.cpp:9-30; SURVEY 8a row a4) as the kernels evaluate them,
+    against the real reference's outputs: only + - * / sqrt => bit-exact."""
+    g = gold("kat_urs")
+    for mode in (0, 1, 2):
+        assert np.array_equal(fvm.kat_urs(g["inp"], 0.02898, 1004.5, mode), g[f"m{mode}"]), mode
+        assert np.array_equal(P.urs(g["inp"], 0.02898, 1004.5, mode), g[f"m{mode}"]), mode
 
 
 def test_kat_newton_cap():
@@ -59,17 +83,27 @@ def test_kat_calc_flux():
     g = gold("kat_calc_flux")
     lax = fvm.kat_calc_flux(f, flux=fvm.FLUX_LAX)
     assert np.array_equal(lax, g["lax"])                  # sqrt only -> bit-exact
-    god = fvm.kat_calc_flux(f, flux=fvm.FLUX_GODUNOV)
     scale = np.abs(g["godunov"]).max(axis=0)
-    assert (np.abs(god - g["godunov"]) / scale).max() < 1e-13
+    for fx in (fvm.FLUX_GODUNOV, 2):                      # 2: through the reduced-instruction solver
+        god = fvm.kat_calc_flux(f, flux=fx)
+        assert (np.abs(god - g["godunov"]) / scale).max() < 1e-13, fx
 
 
+@pytest.mark.parametrize("variant", ["default", "exact_riemann", "pipe"])
 @pytest.mark.parametrize("name", list(pc.CASES))
-def test_run_matches_reference_golden_and_oracle(name):
+def test_run_matches_reference_golden_and_oracle(name, variant):
+    """variant: default = three sweeps + the reduced-instruction Riemann solver; exact_riemann = rim_orig in
+    the reference's operation order; pipe = the pipelined tile kernel (layout 2)."""
     c, spec, st = pc.build(name)
     g = gold(name)
     exact = spec["flux"] == 1          # Lax-Friedrichs: no transcendental functions
     s = fvm.Solver(c.mesh, c.task, spec["flux"], spec["order"])
+    if variant == "exact_riemann":
+        if exact:
+            pytest.skip("Lax-Friedrichs case: no Riemann solver")
+        s.use_exact_riemann(True)
+    if variant == "pipe":
+        s.use_fused(2)
     s.set_state(*st)
     tau = s.calc_time_step()
     assert tau == float(g["tau"])
@@ -79,7 +113,9 @@ def test_run_matches_reference_golden_and_oracle(name):
     if exact:
         assert np.array_equal(flux, g["flux0"])
     else:
-        assert (np.abs(flux - g["flux0"]) / np.abs(g["flux0"]).max(axis=0)).max() < 1e-13
+        ef = (np.abs(flux - g["flux0"]) / np.abs(g["flux0"]).max(axis=0)).max()
+        print(f"{name} [{variant}]: edge-flux rel. error vs reference {ef:.2e}")
+        assert ef < 1e-13, ef
     n = int(g["nsteps"])
     for tag, k in (("mid", n // 2), ("fin", n - n // 2)):
         s.step(k)
@@ -92,6 +128,7 @@ def test_run_matches_reference_golden_and_oracle(name):
                 assert np.array_equal(a, b), (name, tag)
         else:
             e = pc.err_norm((ro, ru, rv, re), ref)
+            print(f"{name} [{variant}] {tag}: rel. Linf per variable vs reference {e}")
             assert max(e) < TOL, (name, tag, e)
             if spec.get("steady"):
                 assert relerr(ct, g[f"{tag}_ctau"]) < TOL
@@ -148,6 +185,110 @@ def test_fused_stage_kernel_equals_three_sweeps_bitwise(flux, order, tile, nt, h
     assert (outs[0][5] != 0).any()                      # the remediation path was exercised
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("flux,order", [(0, 2), (0, 1), (1, 2), (1, 1)])
+@pytest.mark.parametrize("tile,nt,hilbert,exact", [(32, 128, 1, 0), (104, 256, 1, 1), (512, 384, 0, 0), (700, 512, 1, 0)])
+def test_pipe_stage_kernel_equals_three_sweeps_bitwise(flux, order, tile, nt, hilbert, exact, monkeypatch):
+    """k_stage_pipe (persistent CTAs, per-tile blobs and state ranges by cp.async.bulk + mbarrier, ring
+    records by cp.async gathers one tile ahead, primitive state recomputed in shared memory) against
+    k_grad + k_flux + k_update: same expressions, same operand order => the same bits, for every tile
+    size / block size / cell order / Riemann variant, two materials, with limit flags tripping."""
+    monkeypatch.setenv("CFD2D_PIPE_TILE", str(tile))
+    monkeypatch.setenv("CFD2D_PIPE_NT", str(nt))
+    monkeypatch.setenv("CFD2D_HILBERT", str(hilbert))
+    monkeypatch.setenv("CFD2D_LF1_CELL", "0")           # first-order LF: compare against the sweeps, not k_cell_lf1
+    c = cases.channel(40, 24, jitter=0.2, shuffle=True, two_materials=True)
+    c.task.p_max = 1.03e5                               # below the initial peak: cells get flagged
+    st = c.smooth_state()
+    outs = []
+    for layout in (2, 0):
+        s = fvm.Solver(c.mesh, c.task, flux, order)
+        s.use_exact_riemann(bool(exact))
+        s.use_fused(layout)
+        s.set_state(*st)
+        s.calc_time_step()
+        s.step(9)
+        s.step(4)
+        outs.append(s.get_state())
+        s.close()
+    assert (outs[0][5] != 0).any()                      # the remediation path was exercised
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)
+
+
+def test_pipe_layout_switches_steady_and_hooks(monkeypatch):
+    """The pipe layout does not maintain the primitive cache W: the consumers outside the step (time
+    step, steady local time step, parity hooks, switching back to the sweeps) must refresh it."""
+    monkeypatch.setenv("CFD2D_PIPE_TILE", "64")
+    c = cases.channel(24, 12, jitter=0.2, shuffle=True)
+    c.task.steady = 1
+    st = c.smooth_state()
+    flag = np.zeros(c.mesh.nc, np.uint32)
+    flag[[3, 77, 300]] = 2                              # frozen cells given by the caller (caller ids)
+    ref = fvm.Solver(c.mesh, c.task)
+    ref.set_state(*st, flag=flag)
+    ref.calc_time_step()
+    s = fvm.Solver(c.mesh, c.task)
+    s.use_fused(2)
+    s.set_state(*st, flag=flag)
+    s.calc_time_step()
+    for n, layout in ((3, 2), (2, 0), (3, 2), (1, 1), (2, 2)):
+        s.use_fused(layout)
+        s.step(n)
+        ref.step(n)
+        for a, b in zip(s.get_state(), ref.get_state()):
+            assert np.array_equal(a, b), layout
+    assert np.array_equal(s.calc_grad(), ref.calc_grad())
+    assert np.array_equal(s.edge_fluxes(), ref.edge_fluxes())
+    s.close(); ref.close()
+
+
+def _flip_edges(m, seed=5):
+    """The same mesh with a random half of the INNER edges re-oriented (c1 <-> c2, n -> -n, Gauss
+    points swapped so they still run along the edge): a legal cfd2d_mesh whose c2 is no longer the
+    higher-numbered cell, i.e. remediateLimCells' ascending in-place sweep now has real dependencies
+    (a flagged cell reads the already-remediated value of a lower-numbered flagged c2-neighbour)."""
+    rng = np.random.default_rng(seed)
+    d = {k: np.array(getattr(m, k), copy=True) for k in ("cell_S", "cell_cx", "cell_cy", "cell_mat", "cell_edges", "edge_c1",
+                                                          "edge_c2", "edge_nx", "edge_ny", "edge_l", "edge_gp", "edge_bc")}
+    flip = (d["edge_c2"] >= 0) & (rng.random(d["edge_c1"].shape[0]) < 0.5)
+    c1 = d["edge_c1"].copy()
+    d["edge_c1"][flip] = d["edge_c2"][flip]
+    d["edge_c2"][flip] = c1[flip]
+    d["edge_nx"][flip] *= -1.0
+    d["edge_ny"][flip] *= -1.0
+    d["edge_gp"][flip] = d["edge_gp"][flip][:, [2, 3, 0, 1]]
+    return d
+
+
+@pytest.mark.parametrize("fused", [0, 1, 2])
+def test_remediation_sweep_order_on_general_edge_orientation(fused, monkeypatch):
+    """remediateLimCells (fvm_tvd.cpp:464-499) is an in-place ascending sweep.  With the reference
+    readers' c1 < c2 meshes a flagged cell only ever reads not-yet-swept neighbours; here half of the
+    edges are flipped, so the wavefront kernel's dependency rounds are exercised.  Checker: the C
+    oracle's serial sweep.  Lax-Friedrichs order 2 => bit-exact."""
+    monkeypatch.setenv("CFD2D_TILE", "96")
+    c = cases.channel(40, 24, jitter=0.2, shuffle=True)
+    c.task.p_max = 1.03e5                                # below the initial peak: a cluster of adjacent cells trips
+    st = c.smooth_state()
+    m = _flip_edges(c.mesh)
+    s = fvm.Solver(m, c.task, fvm.FLUX_LAX, 2)
+    s.use_fused(fused)
+    o = P.OracleSolver(m, c.task, fvm.FLUX_LAX, 2)
+    for x in (s, o):
+        x.set_state(*st)
+        x.calc_time_step()
+    seen = 0
+    for _ in range(4):
+        s.step(5)
+        o.step(5)
+        got, ref = s.get_state(), o.get_state()
+        seen = max(seen, int(((ref[5] & 2) > 0).sum()))
+        for k in range(6):
+            assert np.array_equal(got[k], ref[k]), k
+    assert seen >= 10                                    # adjacent flagged cells were really swept
+    s.close(); o.close()
 
 
 def test_fused_steady_and_flag_io_roundtrip(monkeypatch):

@@ -56,6 +56,13 @@ def test_calc_flux_kat():
     assert np.array_equal(P.calc_flux(f, flux=1), g["lax"])
 
 
+def test_urs_kat():
+    """Material::URS modes 0/1/2 (global.cpp:9-30) against the real reference's outputs."""
+    g = gold("kat_urs")
+    for mode in (0, 1, 2):
+        assert np.array_equal(P.urs(g["inp"], 0.02898, 1004.5, mode), g[f"m{mode}"])
+
+
 def test_newton_cap_reports_instead_of_hanging():
     # SURVEY F3: the reference's Newton loop has no cap; on this strongly receding, almost-vacuum
     # pair it never meets its tolerance.  The port must return -1 instead of hanging.

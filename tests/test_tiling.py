@@ -53,3 +53,42 @@ def test_rank_local_mesh_has_boundary_tiles_and_fixed_halo():
     assert sorted(perm[:rm.nc].tolist()) == list(range(rm.nc))
     assert st["boundary"] >= 1 and st["interior"] >= 1
     assert st["interior"] + st["boundary"] == st["ntiles"]
+
+
+# ---- the pipelined tile kernel's plan (layout 2): per-tile blobs --------------------------------
+@pytest.mark.parametrize("make,tc,bins", [
+    (lambda: cases.channel(48, 24, jitter=0.2, shuffle=True, two_materials=True), 64, True),
+    (lambda: cases.channel(48, 24, jitter=0.2, shuffle=True), 128, False),
+    (lambda: cases.forward_step(30, 10, jitter=0.15), 100, True),
+    (lambda: cases.strip(40, 10, jitter=0.2, shuffle=True), 32, False),
+    (lambda: cases.strip(4, 2), 512, True),
+])
+def test_pipe_plan_invariants(make, tc, bins):
+    """Every table k_stage_pipe reads is re-derived from the blob bytes inside cfd2d_pipe_plan."""
+    c = make()
+    st = fvm.pipe_plan(c.mesh, c.task, tile_cells=tc, dir_bins=bins)
+    tc8 = (max(tc, 32) + 7) // 8 * 8
+    assert st["ntiles"] == -(-c.mesh.nc // tc8)
+    assert st["sum_ne"] >= c.mesh.ne
+    assert st["interior"] == st["ntiles"] and st["boundary"] == 0
+    assert st["blob_bytes"] % 16 == 0 and st["blob_max"] % 16 == 0
+
+
+def test_pipe_plan_bytes_per_cell():
+    """The static tables of a stage are ~150 B per cell at 128-cell tiles (64 B per edge, duplicated on
+    tile perimeters, + centres, areas, slots, ring-1 tables) -- the three sweeps read ~290 B."""
+    c = cases.channel(200, 100)
+    st = fvm.pipe_plan(c.mesh, c.task, tile_cells=128, dir_bins=False)
+    assert st["blob_bytes"] / c.mesh.nc < 190.0, st
+    assert st["sum_ring1"] / c.mesh.nc < 0.45 and st["sum_ring2"] / c.mesh.nc < 0.55, st
+    st256 = fvm.pipe_plan(c.mesh, c.task, tile_cells=256, dir_bins=False)
+    assert st256["blob_bytes"] < st["blob_bytes"]
+
+
+def test_pipe_plan_rank_local_mesh():
+    c = cases.channel(64, 32, jitter=0.1)
+    part = decomp.slab_part(c.mesh, 2)
+    rm = decomp.decompose(c.mesh, part, 2, only_rank=0)[0]
+    st = fvm.pipe_plan(rm.local, c.task, tile_cells=128, nc_owned=rm.nc)
+    assert st["boundary"] >= 1 and st["interior"] >= 1
+    assert st["interior"] + st["boundary"] == st["ntiles"]
