@@ -437,13 +437,20 @@ static pipe_fn pipe_kernel_nt(int flux, int order, int stage) {
     return stage == 1 ? (pipe_fn)k_stage_pipe<1, 1, 1, NT, MINB> : (pipe_fn)k_stage_pipe<1, 1, 2, NT, MINB>;
 }
 
+// (threads per CTA, min resident CTAs per SM) pairs that are compiled: the second number caps the
+// registers (65536 / (NT * MINB)), the shared memory of the tile decides what is really resident
 static pipe_fn pipe_kernel(const cfd2d_fvm* h, int stage) {
-    const int fx = flux_variant(h);
-    switch (h->pipe_nt) {
-        case 128: return pipe_kernel_nt<128, 4>(fx, h->ctrl.order, stage);
-        case 384: return pipe_kernel_nt<384, 1>(fx, h->ctrl.order, stage);
-        case 512: return pipe_kernel_nt<512, 1>(fx, h->ctrl.order, stage);
-        default:  return pipe_kernel_nt<256, 2>(fx, h->ctrl.order, stage);
+    const int fx = flux_variant(h), od = h->ctrl.order;
+    switch (h->pipe_nt * 10 + h->pipe_minb) {
+        case 1284:  return pipe_kernel_nt<128, 4>(fx, od, stage);
+        case 2563:  return pipe_kernel_nt<256, 3>(fx, od, stage);
+        case 3841:  return pipe_kernel_nt<384, 1>(fx, od, stage);
+        case 3842:  return pipe_kernel_nt<384, 2>(fx, od, stage);
+        case 5121:  return pipe_kernel_nt<512, 1>(fx, od, stage);
+        case 5122:  return pipe_kernel_nt<512, 2>(fx, od, stage);
+        case 7681:  return pipe_kernel_nt<768, 1>(fx, od, stage);
+        case 10241: return pipe_kernel_nt<1024, 1>(fx, od, stage);
+        default:    return pipe_kernel_nt<256, 2>(fx, od, stage);
     }
 }
 
@@ -632,8 +639,18 @@ static int build_pipe_plan_dev(cfd2d_fvm* h) {
     if (const char* ev = getenv("CFD2D_PIPE_TILE")) TC = atoi(ev);
     h->pipe_nt = 256;
     if (const char* ev = getenv("CFD2D_PIPE_NT")) h->pipe_nt = atoi(ev);
-    if (h->pipe_nt != 128 && h->pipe_nt != 256 && h->pipe_nt != 384 && h->pipe_nt != 512) h->pipe_nt = 256;
-    h->pipe_minb = h->pipe_nt == 128 ? 4 : (h->pipe_nt == 256 ? 2 : 1);
+    h->pipe_minb = 0;
+    if (const char* ev = getenv("CFD2D_PIPE_MINB")) h->pipe_minb = atoi(ev);
+    {
+        static const int ok[][2] = {{128, 4}, {256, 2}, {256, 3}, {384, 1}, {384, 2}, {512, 1}, {512, 2}, {768, 1}, {1024, 1}};
+        bool found = false, nt_known = false;
+        int first_minb = 0;
+        for (auto& o : ok) {
+            if (o[0] == h->pipe_nt) { if (!nt_known) first_minb = o[1]; nt_known = true; if (o[1] == h->pipe_minb) found = true; }
+        }
+        if (!nt_known) { h->pipe_nt = 256; h->pipe_minb = 2; }
+        else if (!found) h->pipe_minb = first_minb;
+    }
     PipePlan pp;
     // Godunov: edges of a tile grouped by normal direction (branch coherence of rim_orig); LF: by cell id
     std::string perr = build_pipe_plan(*h->pm, TC, h->ctrl.flux == CFD2D_FLUX_GODUNOV, pp);
@@ -660,7 +677,7 @@ static int build_pipe_plan_dev(cfd2d_fvm* h) {
     Q.so_ring = o; o += 32 * (pp.nring_max > 0 ? pp.nring_max : 1);
     Q.so_gx = o; o += 64 * (pp.nhalo_max > 0 ? pp.nhalo_max : 1);
     Q.stage_bytes = up(o, 128);
-    Q.o_stage0 = 128;
+    Q.o_stage0 = PIPE_HDR_BYTES;
     int q = Q.o_stage0 + 2 * Q.stage_bytes;
     Q.nl2_max = pp.nl2_max; Q.nl_max = pp.nl_max; Q.ne_max = pp.ne_max;
     Q.o_W0 = q; q += 16 * pp.nl2_max;

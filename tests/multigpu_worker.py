@@ -14,6 +14,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     os.environ.setdefault("CFD2D_TILE", "128")      # several interior + boundary tiles per rank on this small mesh
+    os.environ.setdefault("CFD2D_PIPE_TILE", "96")
     import torch
     import torch.distributed as dist
     from cfd2d_b200 import cases, decomp, fvm
@@ -22,9 +23,10 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
     # step layouts of a multi-rank handle: three sweeps with the halo exchange overlapped on the comm
-    # stream (default), the same serialised on one stream, and the tile-fused stage kernel
+    # stream (default), the same serialised on one stream, the tile-fused stage kernel, and the
+    # pipelined tile kernel (interior tiles under the exchanges, boundary tiles after them)
     modes = {"overlap": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1"}, "serial": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "0"},
-             "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1"}}
+             "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1"}, "pipe": {"CFD2D_FUSED": "2", "CFD2D_OVERLAP": "1"}}
     # (partition, flux, order, steady, p_max): the last two cases lower the pressure limit below the
     # initial peak so that a blob of adjacent cells trips the limiter ACROSS the partition cut:
     # remediateLimCells (fvm_tvd.cpp:464-499) then rewrites send cells after the end-of-step exchange

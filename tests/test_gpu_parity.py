@@ -188,7 +188,7 @@ def test_fused_stage_kernel_equals_three_sweeps_bitwise(flux, order, tile, nt, h
 
 
 @pytest.mark.parametrize("flux,order", [(0, 2), (0, 1), (1, 2), (1, 1)])
-@pytest.mark.parametrize("tile,nt,hilbert,exact", [(32, 128, 1, 0), (104, 256, 1, 1), (512, 384, 0, 0), (700, 512, 1, 0)])
+@pytest.mark.parametrize("tile,nt,hilbert,exact", [(32, 128, 1, 0), (104, 256, 1, 1), (64, 384, 0, 0), (320, 512, 1, 0)])
 def test_pipe_stage_kernel_equals_three_sweeps_bitwise(flux, order, tile, nt, hilbert, exact, monkeypatch):
     """k_stage_pipe (persistent CTAs, per-tile blobs and state ranges by cp.async.bulk + mbarrier, ring
     records by cp.async gathers one tile ahead, primitive state recomputed in shared memory) against

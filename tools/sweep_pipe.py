@@ -17,7 +17,8 @@ def main():
     ap.add_argument("--nx", type=int, default=2000)
     ap.add_argument("--ny", type=int, default=1000)
     ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--pipe", default="128:256:0,96:256:0,192:384:0,256:512:0,128:128:0,128:256:1", help="TC:NT:CTAS list (CTAS 0 = all that fit)")
+    ap.add_argument("--pipe", default="128:256:2,128:384:2,128:512:2,256:512:1,256:768:1,256:1024:1,192:768:1",
+                    help="TC:NT:MINB list (tile cells : threads per CTA : launch-bounds min CTAs per SM)")
     ap.add_argument("--variants", default="0:2,1:2,1:1,0:1")
     ap.add_argument("--skip-base", action="store_true")
     a = ap.parse_args()
@@ -70,10 +71,10 @@ def main():
                 run("sweeps_no_lf1cell", flux, order, 0, env={"CFD2D_LF1_CELL": 0})
                 os.environ["CFD2D_LF1_CELL"] = "1"
         for cfg in a.pipe.split(","):
-            tc, nt, ctas = (int(x) for x in cfg.split(":"))
-            run("pipe", flux, order, 2, env={"CFD2D_PIPE_TILE": tc, "CFD2D_PIPE_NT": nt, "CFD2D_PIPE_CTAS": ctas})
+            tc, nt, minb = (int(x) for x in cfg.split(":"))
+            run("pipe", flux, order, 2, env={"CFD2D_PIPE_TILE": tc, "CFD2D_PIPE_NT": nt, "CFD2D_PIPE_MINB": minb})
         if flux == 0 and order == 2:
-            run("pipe_exact_riemann", flux, order, 2, exact=True, env={"CFD2D_PIPE_TILE": 128, "CFD2D_PIPE_NT": 256, "CFD2D_PIPE_CTAS": 0})
+            run("pipe_exact_riemann", flux, order, 2, exact=True, env={"CFD2D_PIPE_TILE": 128, "CFD2D_PIPE_NT": 256, "CFD2D_PIPE_MINB": 2})
 
 
 if __name__ == "__main__":
