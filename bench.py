@@ -252,8 +252,11 @@ def main():
     ap.add_argument("--ny", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra Lax-Friedrichs variant lines")
-    ap.add_argument("--partition", default="slab", choices=["slab", "metis"],
-                    help="N>1: slab (default; O(N) setup) or the bundled METIS as the reference's Decomp (decomp.cpp:104)")
+    ap.add_argument("--partition", default="auto", choices=["auto", "slab", "metis"],
+                    help="N>1: metis = the bundled METIS exactly as the reference's Decomp calls it (decomp.cpp:86-104; every rank "
+                         "builds the global mesh: ~0.6 GB of host memory and ~3.5 s per million cells and rank); slab = equal-count "
+                         "strips built from a window of the mesh (O(cells per rank) setup); auto (default) = metis when the host "
+                         "memory allows it, else slab")
     ap.add_argument("--strong", action="store_true",
                     help="N>1: strong scaling -- the (nx x ny x 2)-cell mesh is the WHOLE job, split N ways "
                          "(BASELINE configs[3]: --nx 8000 --ny 2000 = 32 M cells); default is weak scaling (nx x ny x 2 per GPU)")
@@ -283,6 +286,20 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     flux = 0 if a.flux == "godunov" else 1
+    partition_note = None
+    if world > 1 and a.partition == "auto":
+        # METIS needs the global dual graph on every rank: bound the host memory before choosing it
+        total_mcells = 2.0 * a.nx * a.ny * (1 if a.strong else world) / 1e6
+        need_gb = 0.62 * total_mcells * world
+        try:
+            avail_gb = [float(ln.split()[1]) / 1e6 for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0]
+        except Exception:
+            avail_gb = 0.0
+        from cfd2d_b200 import decomp as _d
+        have = os.path.exists(_d.METIS_LIB)
+        a.partition = "metis" if (have and need_gb < 0.6 * avail_gb) else "slab"
+        partition_note = (f"auto: {a.partition} (global mesh on every rank needs ~{need_gb:.0f} GB of host memory, "
+                          f"{avail_gb:.0f} GB available, bundled METIS {'found' if have else 'missing'})")
     clocks = ClockSampler(local)      # started now: nvidia-smi needs a few hundred ms before its first sample
     if rank == 0:
         clocks.start()
@@ -302,6 +319,16 @@ def main():
         s, st, nc_local, nc_total = decomp.make_rank_solver(nx_rank, a.ny, rank, world, local, flux, a.order, dist,
                                                             partition=a.partition,
                                                             tiles=max(1, a.nx // 1000) if a.strong else None)
+    halo_stats = None
+    if world > 1:
+        rm = s.rank_mesh
+        hs = torch.tensor([rm.nc_ex - rm.nc, int((np.asarray(rm.recv_count) > 0).sum()), rm.nc], device="cuda", dtype=torch.int64)
+        hall = [torch.zeros_like(hs) for _ in range(world)]
+        dist.all_gather(hall, hs)
+        hall = torch.stack(hall).cpu().numpy()
+        halo_stats = {"halo_cells_per_rank": hall[:, 0].tolist(), "peers_per_rank": hall[:, 1].tolist(),
+                      "owned_cells_per_rank": hall[:, 2].tolist(),
+                      "bytes_per_exchange_max": {"state_32B": int(32 * hall[:, 0].max()), "gradients_64B": int(64 * hall[:, 0].max())}}
     if a.fused and a.layout is None:
         a.layout = 1
     if a.layout is not None:
@@ -363,7 +390,7 @@ def main():
                              "fluxes + residual gather + update, the 'residual+update' of the north star): "
                              "320 algorithmic B/cell x owned cells / average launch duration (CUDA events on the launching stream)",
                     "stage_ms": stage_ms,
-                    "dominant_kernel": {"name": "k_stage", "avg_ms": stage_ms, "share_of_step": 2 * stage_ms / (ms / a.steps),
+                    "dominant_kernel": {"name": "k_stage_pipe" if a.layout == 2 else "k_stage", "avg_ms": stage_ms, "share_of_step": 2 * stage_ms / (ms / a.steps),
                                         "algorithmic_bytes_per_cell": ALGO_BYTES_STAGE, "achieved": ach_stage,
                                         "frac": ach_stage / peak},
                     "per_kernel": per_kernel, "plan": s.plan_summary}
@@ -385,17 +412,37 @@ def main():
                                         "achieved": ach_dom, "frac": ach_dom / peak},
                     "per_kernel": per_kernel}
     # measured DRAM traffic (ncu --set full capture of this command at 4 M cells, Godunov order 2; per launch)
-    tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
+    tp = os.path.join(ROOT, "profiles", "traffic_r02.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "traffic_r01.json")
     if os.path.exists(tp) and nc_local == 4000000 and flux == 0 and a.order == 2:
         try:
             tr = json.load(open(tp))
             pk = tr["per_kernel_dram_bytes_4m"]
             if fused:
-                roofline["traffic"] = 0.5 * (pk["stage1_fused"] + pk["stage2_fused"])
+                sfx = "pipe" if a.layout == 2 else "fused"
+                roofline["traffic"] = 0.5 * (pk["stage1_" + sfx] + pk["stage2_" + sfx])
             else:
                 roofline["traffic"] = tr["stage_dram_bytes_4m"]
                 roofline["dominant_kernel"]["traffic"] = pk.get(roofline["dominant_kernel"]["name"][2:])
             roofline["traffic_source"] = tr["source"]
+        except Exception:
+            pass
+
+    # FP64-pipe roofline of the flux kernel (the exact Riemann solver is FP64-issue bound, so the HBM
+    # fraction alone does not describe it): FP64 instructions per launch from the committed ncu capture of this
+    # command, divided by the LIVE k_flux time; peak = 64 FP64 lanes x SMs x max SM clock (ncu: dfma peak_sustained = 64)
+    fp = os.path.join(ROOT, "profiles", "fp64_r02.json")
+    if os.path.exists(fp) and nc_local == 4000000 and flux == 0 and a.order == 2 and not fused and not a.exact_riemann:
+        try:
+            fj = json.load(open(fp))
+            sm_mhz = (clk or {}).get("sm_max_mhz") or 1965.0
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            peak64 = 64.0 * sms * sm_mhz * 1e6
+            ach64 = fj["k_flux_fp64_thread_inst_per_launch_4m"] / (flux_ms * 1e-3)
+            roofline["fp64"] = {"bound": "fp64", "kernel": "k_flux<2,2>", "achieved": ach64 / 1e12, "peak": peak64 / 1e12,
+                                "unit": "T FP64 inst/s", "frac": ach64 / peak64,
+                                "ncu_pipe_fp64_pct": fj["k_flux_pipe_fp64_cycles_active_pct"], "source": fj["source"]}
         except Exception:
             pass
 
@@ -428,12 +475,59 @@ def main():
            "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
            "what": "cfd2d_fvm_set_state(pinned host) + cfd2d_fvm_step(1) + cfd2d_fvm_get_state(pinned host) per step",
            "host_binding": numa}
+    # the ceiling of that call pattern: the same bytes moved by bare cudaMemcpyAsync (no kernels), all ranks at once
+    try:
+        dbuf = [torch.empty(nc_local, dtype=torch.float64, device="cuda") for _ in range(4)]
+        def copies():
+            for d_, h_ in zip(dbuf, pin):
+                d_.copy_(h_, non_blocking=True)
+            for h_, d_ in zip(out, dbuf):
+                h_.copy_(d_, non_blocking=True)
+            torch.cuda.synchronize()
+        copies()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copies()
+        barrier()
+        cp_s = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([cp_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cp_s = float(t.item())
+        e2e["copy_only_ms_per_step"] = 1e3 * cp_s / e2e_steps
+        e2e["copy_only_GBps_per_rank"] = 64.0 * nc_local * e2e_steps / cp_s / 1e9
+        e2e["copy_ceiling_note"] = ("H2D then D2H of the same pinned buffers with no kernels, all ranks concurrently: what the "
+                                    "host <-> device path of this box gives this call pattern")
+        del dbuf
+    except Exception as ex:
+        e2e["copy_only_error"] = repr(ex)
+    # the Method glue's real cadence: state up once, FILE_OUTPUT_STEP steps on the device, state down once
+    cad = 10
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        s.set_state(*ptr_in)
+        s.step(cad)
+        s.get_state(out=ptr_out, want_tau=False, want_flag=False)
+    barrier()
+    cad_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([cad_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cad_s = float(t.item())
+    e2e["at_output_cadence"] = {"steps_between_transfers": cad, "value": nc_total * 2.0 * cad * 3 / cad_s, "unit": "cell-updates/s",
+                                "what": "set_state + step(10) + get_state, i.e. FILE_OUTPUT_STEP = 10 in task.xml"}
 
     line = {"metric": "cell-updates/sec (FP64, RK stage)", "value": value, "unit": "cell-updates/s", "n_gpus": world,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True,
             "scaling": "strong" if (a.strong and world > 1) else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(a), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "setup_s": setup_s}
+    if halo_stats is not None:
+        line["halo"] = halo_stats
+    if partition_note:
+        line["config"]["partition_note"] = partition_note
 
     # ---- the bandwidth-bound variants of the same path (reference's Lax-Friedrichs block), N=1 only
     if world == 1 and not a.no_variants and flux == 0:

@@ -31,6 +31,13 @@ struct cfd2d_fvm {
     std::vector<void*> allocs;
     double4 *Ua = nullptr, *Ub = nullptr, *W = nullptr, *Wb = nullptr, *G = nullptr, *F = nullptr;
     uint32_t* io_u32 = nullptr;   // flag staging (caller order)
+    // asynchronous snapshot for FVM_TVD::save (cfd2d_fvm_snapshot_begin / _end)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_snap = nullptr, ev_snap_done = nullptr;
+    double* snap_host = nullptr;   // pinned: 5 x nc doubles (ro, ru, rv, re, cTau) + nc uint32 flags
+    bool snap_pending = false;
+    char* gather_buf = nullptr;    // cfd2d_fvm_gather_state staging (device)
+    size_t gather_cap = 0;
     double* grad_tmp = nullptr;   // parity hook staging (cfd2d_fvm_calc_grad), allocated on first use
     // tile-fused stage kernel (fvm_fused.cuh)
     bool fused = true;
@@ -442,6 +449,7 @@ static pipe_fn pipe_kernel_nt(int flux, int order, int stage) {
 static pipe_fn pipe_kernel(const cfd2d_fvm* h, int stage) {
     const int fx = flux_variant(h), od = h->ctrl.order;
     switch (h->pipe_nt * 10 + h->pipe_minb) {
+#ifndef CFD2D_PIPE_FEW      /* kernel-variant sweeps: build only the default shape */
         case 1284:  return pipe_kernel_nt<128, 4>(fx, od, stage);
         case 2563:  return pipe_kernel_nt<256, 3>(fx, od, stage);
         case 3841:  return pipe_kernel_nt<384, 1>(fx, od, stage);
@@ -450,6 +458,7 @@ static pipe_fn pipe_kernel(const cfd2d_fvm* h, int stage) {
         case 5122:  return pipe_kernel_nt<512, 2>(fx, od, stage);
         case 7681:  return pipe_kernel_nt<768, 1>(fx, od, stage);
         case 10241: return pipe_kernel_nt<1024, 1>(fx, od, stage);
+#endif
         default:    return pipe_kernel_nt<256, 2>(fx, od, stage);
     }
 }
@@ -771,6 +780,19 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     }
     for (int i = 0; i < nc_ex; i++)
         if (m->cell_mat[i] < 0 || m->cell_mat[i] >= p->nmat) { g_create_error = "cell material index out of range"; return CFD2D_EINVAL; }
+    // The per-cell slot order IS the summation order of the residual and of the gradients; the reference's
+    // edge-ordered scatter (fvm_tvd.cpp:253-292, :353-363) corresponds to ascending edge ids, which its readers
+    // produce (MeshReaderSalomeUnv.cpp:176-177,193-194).  A caller with another order would silently get
+    // different bits, so the documented contract is enforced.
+    for (int i = 0; i < nc; i++) {
+        const int32_t* ce = m->cell_edges + 3 * (size_t)i;
+        if (!(ce[0] < ce[1] && ce[1] < ce[2])) {
+            char b[160];
+            snprintf(b, sizeof b, "cell_edges of cell %d is not in ascending edge id (%d, %d, %d): the slot order is the summation order", i, ce[0], ce[1], ce[2]);
+            g_create_error = b;
+            return CFD2D_EINVAL;
+        }
+    }
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
@@ -1088,6 +1110,11 @@ void cfd2d_fvm_destroy(cfd2d_fvm* h) {
     if (h->ev_stage) cudaEventDestroy(h->ev_stage);
     if (h->ev_U) cudaEventDestroy(h->ev_U);
     if (h->comm) { cudaStreamSynchronize(h->comm); cudaStreamDestroy(h->comm); }
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->ev_snap) cudaEventDestroy(h->ev_snap);
+    if (h->ev_snap_done) cudaEventDestroy(h->ev_snap_done);
+    if (h->snap_host) cudaFreeHost(h->snap_host);
+    if (h->gather_buf) cudaFree(h->gather_buf);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1405,6 +1432,102 @@ int cfd2d_fvm_get_state(cfd2d_fvm* h, double* ro, double* ru, double* rv, double
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+// ---- FVM_TVD::save without stalling the time loop ---------------------------
+// begin: the state (caller order), cTau and the flags are unpacked on the compute stream into the
+// handle's staging arrays -- ordered before whatever steps the caller enqueues next -- and copied to
+// pinned host memory by a SEPARATE copy stream, so the D2H transfer and the caller's VTK writer run
+// under the next chunk of steps.  end: waits for the copy and hands the arrays to the caller.
+int cfd2d_fvm_snapshot_begin(cfd2d_fvm* h) {
+    if (!h) return CFD2D_EINVAL;
+    if (h->snap_pending) { h->error = "snapshot_begin: the previous snapshot was not collected (snapshot_end)"; return CFD2D_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t nc = (size_t)h->nc, nb = nc * sizeof(double);
+    if (!h->copy_stream) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_snap, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&h->ev_snap_done, cudaEventDisableTiming));
+        CUDA_TRY(h, cudaHostAlloc((void**)&h->snap_host, (5 * nb + nc * sizeof(uint32_t)) + 64, cudaHostAllocDefault));
+    }
+    if (h->nc) {
+        h->launches += 3;
+        k_unpack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->Ua, h->io[0], h->io[1], h->io[2], h->io[3]);
+        k_gather_perm<double><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->P.ctau, h->io[4]);
+        k_gather_perm<uint32_t><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->P.flag, h->io_u32);
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_snap, h->stream));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_snap, 0));
+    for (int i = 0; i < 5; i++)
+        if (nb) CUDA_TRY(h, cudaMemcpyAsync(h->snap_host + (size_t)i * nc, h->io[i], nb, cudaMemcpyDeviceToHost, h->copy_stream));
+    if (nc) CUDA_TRY(h, cudaMemcpyAsync(h->snap_host + 5 * nc, h->io_u32, nc * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->copy_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_snap_done, h->copy_stream));
+    // the staging arrays are reused by set_state / get_state / get_primitive: those wait for the copy
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_snap_done, 0));
+    h->snap_pending = true;
+    return 0;
+}
+
+int cfd2d_fvm_snapshot_end(cfd2d_fvm* h, double* ro, double* ru, double* rv, double* re, double* cTau, uint32_t* flag) {
+    if (!h) return CFD2D_EINVAL;
+    if (!h->snap_pending) { h->error = "snapshot_end without snapshot_begin"; return CFD2D_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaEventSynchronize(h->ev_snap_done));
+    h->snap_pending = false;
+    const size_t nc = (size_t)h->nc, nb = nc * sizeof(double);
+    double* dst[5] = {ro, ru, rv, re, cTau};
+    for (int i = 0; i < 5; i++) if (dst[i] && nb) memcpy(dst[i], h->snap_host + (size_t)i * nc, nb);
+    if (flag && nc) memcpy(flag, h->snap_host + 5 * nc, nc * sizeof(uint32_t));
+    return 0;
+}
+
+// Multi-rank: the owned-cell state of every rank collected on `root` (what a parallel Method does with
+// Parallel::send/recv before the root writes the result file).  Rank-major concatenation on root.
+int cfd2d_fvm_gather_state(cfd2d_fvm* h, int root, const int32_t* counts, double* ro, double* ru, double* rv, double* re,
+                           double* cTau, uint32_t* flag) {
+    if (!h || !counts) return CFD2D_EINVAL;
+    if (!h->halo) { h->error = "gather_state needs a multi-rank handle"; return CFD2D_EINVAL; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int nr = halo_nranks(h->halo), me = halo_rank(h->halo);
+    if (counts[me] != h->nc) { h->error = "gather_state: counts[rank] != owned cells of this handle"; return CFD2D_EINVAL; }
+    const size_t REC = 5 * sizeof(double) + sizeof(uint32_t);          // bytes per cell: ro ru rv re cTau | flag
+    std::vector<size_t> bytes(nr), off(nr + 1, 0);
+    for (int p = 0; p < nr; p++) { bytes[p] = (size_t)counts[p] * REC; off[p + 1] = off[p] + bytes[p]; }
+    const size_t need = (me == root ? off[nr] : bytes[me]) + 16;
+    if (h->gather_cap < need) {
+        if (h->gather_buf) cudaFree(h->gather_buf);
+        h->gather_buf = nullptr; h->gather_cap = 0;
+        CUDA_TRY(h, cudaMalloc((void**)&h->gather_buf, need));
+        h->gather_cap = need;
+    }
+    char* mine = h->gather_buf + (me == root ? off[me] : 0);
+    const size_t nc = (size_t)h->nc, nb = nc * sizeof(double);
+    if (nc) {
+        h->launches += 3;
+        k_unpack_state<<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->Ua, h->io[0], h->io[1], h->io[2], h->io[3]);
+        k_gather_perm<double><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->P.ctau, h->io[4]);
+        k_gather_perm<uint32_t><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->nc, h->P.c_perm, h->P.flag, h->io_u32);
+        for (int i = 0; i < 5; i++) CUDA_TRY(h, cudaMemcpyAsync(mine + (size_t)i * nb, h->io[i], nb, cudaMemcpyDeviceToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(mine + 5 * nb, h->io_u32, nc * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int rc = halo_gather_bytes(h->halo, root, mine, bytes[me], h->gather_buf, bytes.data(), h->comm);   // NCCL traffic: comm stream
+    if (rc) { h->error = halo_error(h->halo); return rc; }
+    CUDA_TRY(h, cudaStreamSynchronize(h->comm));
+    if (me == root) {
+        std::vector<char> host(off[nr]);
+        CUDA_TRY(h, cudaMemcpy(host.data(), h->gather_buf, off[nr], cudaMemcpyDeviceToHost));
+        size_t c0 = 0;
+        double* dst[5] = {ro, ru, rv, re, cTau};
+        for (int p = 0; p < nr; p++) {
+            const size_t n = (size_t)counts[p];
+            const char* b = host.data() + off[p];
+            for (int i = 0; i < 5; i++) if (dst[i] && n) memcpy(dst[i] + c0, b + (size_t)i * n * sizeof(double), n * sizeof(double));
+            if (flag && n) memcpy(flag + c0, b + 5 * n * sizeof(double), n * sizeof(uint32_t));
+            c0 += n;
+        }
+    }
     return 0;
 }
 

@@ -208,6 +208,9 @@ __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const 
 #ifndef CFD2D_FLUX_MINB
 #define CFD2D_FLUX_MINB 8
 #endif
+#ifndef CFD2D_FLUX_PRELOAD
+#define CFD2D_FLUX_PRELOAD 0
+#endif
 
 template <int FLUX, int ORDER>
 #ifndef CFD2D_FLUXLF_MINB
@@ -225,6 +228,46 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
     if (!live) e = e1 - 1;
     int2 cc = __ldg(P.e_c + e);
     double2 n = __ldg(P.e_n + e);
+#if CFD2D_FLUX_PRELOAD
+    // All gathers of BOTH cells are issued before any arithmetic (a boundary edge re-reads its own cell:
+    // same sectors, no extra traffic), so the kernel pays one exposed gather latency per thread instead
+    // of two; the records are consumed straight into the two reconstructed states.
+    const bool inner = cc.y >= 0;
+    const int c2i = inner ? cc.y : cc.x;
+    double4 w1 = ld4(W, cc.x), w2 = ld4(W, c2i);
+    double4 ga1, gb1, ga2, gb2;
+    double2 d1, d2;
+    double EL = 0.0, ER = 0.0;
+    if (ORDER == 2) {
+        ga1 = ld4(G, 2 * cc.x); gb1 = ld4(G, 2 * cc.x + 1);
+        ga2 = ld4(G, 2 * c2i); gb2 = ld4(G, 2 * c2i + 1);
+        d1 = __ldg(reinterpret_cast<const double2*>(P.e_d1 + e) + gp);
+        d2 = __ldg(reinterpret_cast<const double2*>(P.e_d2 + e) + gp);
+    }
+    if (FLUX == 1) {
+        double4 u1 = ld4(Ucur, cc.x), u2 = ld4(Ucur, c2i);
+        EL = u1.w / u1.x; ER = u2.w / u2.x;
+    }
+    Prim L = {w1.x, w1.y, w1.z, w1.w};
+    Prim R = {w2.x, w2.y, w2.z, w2.w};
+    double T1 = 0.0;
+    MatC m;
+    if (!inner) { m = get_mat(P, cc.x); T1 = prim_T(L, m); }   // cell-centre T, before extrapolation
+    if (ORDER == 2) {
+        L.r += ga1.x * d1.x + ga1.y * d1.y;
+        L.p += ga1.z * d1.x + ga1.w * d1.y;
+        L.u += gb1.x * d1.x + gb1.y * d1.y;
+        L.v += gb1.z * d1.x + gb1.w * d1.y;
+        R.r += ga2.x * d2.x + ga2.y * d2.y;
+        R.p += ga2.z * d2.x + ga2.w * d2.y;
+        R.u += gb2.x * d2.x + gb2.y * d2.y;
+        R.v += gb2.z * d2.x + gb2.w * d2.y;
+    }
+    if (!inner) {
+        int ib = __ldg(P.e_bc + e);
+        R = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
+    }
+#else
     double4 w1 = ld4(W, cc.x);
     Prim L = {w1.x, w1.y, w1.z, w1.w};
     Prim R;
@@ -260,6 +303,7 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
         int ib = __ldg(P.e_bc + e);
         R = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
     }
+#endif
     double f0, f1, f2, f3;
     if (FLUX == 0) {
         int it = flux_godunov_dev(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);

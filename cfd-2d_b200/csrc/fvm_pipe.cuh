@@ -89,6 +89,9 @@ __device__ __forceinline__ void pipe_issue_tile(const KParams& P, const PParams&
 
 #define PIPE_HDR_BYTES 640      // [0,16) two mbarriers | [32,272) three PipeTile slots | [288,544) up to 8 materials
 #define PIPE_MAT_SMEM 8
+#ifndef PIPE_LF_BOTH_GP
+#define PIPE_LF_BOTH_GP 0      // 1: LF flux phase = one thread per edge, both Gauss points (measured: see profiles/README.md)
+#endif
 
 // reconstruction of one side at one Gauss point (FVM_TVD::reconstruct, fvm_tvd.cpp:646-691)
 __device__ __forceinline__ Prim pipe_recon(const double2 wa, const double2 wb, const double2 a, const double2 b,
@@ -320,7 +323,7 @@ k_stage_pipe(KParams P, PParams Q, const double4* Uin, double4* Uout, const doub
         }
 
         // ---------------- phase F: reconstruction + numerical flux (k_flux arithmetic) ------------
-        if (FLUX == 1) {
+        if (FLUX == 1 && PIPE_LF_BOTH_GP) {
             // one thread per edge, both Gauss points
             for (int q = tid; q < ne_t; q += NT) {
                 const double2 n = e_n[q], lc = e_l[q];
@@ -379,6 +382,8 @@ k_stage_pipe(KParams P, PParams Q, const double4* Uin, double4* Uout, const doub
                 const double2 wa = W0[l1], wb = W1[l1];
                 Prim L = {wa.x, wa.y, wb.x, wb.y};
                 Prim Rr;
+                double EL = 0.0, ER = 0.0;
+                if (FLUX == 1) EL = Es[l1];
                 double T1 = 0.0;
                 MatC m;
                 if (!inner) { m = mat_of(l1); T1 = prim_T(L, m); }   // cell-centre T, before extrapolation
@@ -389,18 +394,20 @@ k_stage_pipe(KParams P, PParams Q, const double4* Uin, double4* Uout, const doub
                 if (inner) {
                     const double2 va = W0[l2], vb = W1[l2];
                     Rr.r = va.x; Rr.p = va.y; Rr.u = vb.x; Rr.v = vb.y;
+                    if (FLUX == 1) ER = Es[l2];
                     if (ORDER == 2) {
                         const double2 c2 = cxy[l2];
                         Rr = pipe_recon(va, vb, G0[l2], G1[l2], G2[l2], G3[l2], pe.x - c2.x, pe.y - c2.y);
                     }
                 } else {
                     const int ib = l2 & 0xff;
-                    Rr = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, nullptr);
+                    Rr = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
                 }
                 double f0, f1, f2, f3;
-                int it;
+                int it = 0;
                 if (FLUX == 0) it = flux_godunov_dev(P.rim, P.max_newton, L, Rr, n.x, n.y, f0, f1, f2, f3);
-                else it = flux_godunov_fast(P.rim, P.max_newton, L, Rr, n.x, n.y, f0, f1, f2, f3);
+                else if (FLUX == 2) it = flux_godunov_fast(P.rim, P.max_newton, L, Rr, n.x, n.y, f0, f1, f2, f3);
+                else flux_lax_dev(P.rim.GAM, L, EL, Rr, ER, n.x, n.y, f0, f1, f2, f3);
                 // perimeter edges are evaluated by two tiles: a Newton-cap hit counts once per evaluation
                 if (it < 0 && live) atomicAdd(P.err, 1);
                 double a = gp ? f2 : f0, bq = gp ? f3 : f1;      // mine

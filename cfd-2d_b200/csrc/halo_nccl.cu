@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(256) k_pack_records(int n, int rec4, const int
 
 typedef struct { char internal[128]; } nccl_uid_t;
 typedef void* nccl_comm_t;
-enum { NCCL_FLOAT64 = 8, NCCL_MIN = 3 };
+enum { NCCL_UINT8 = 1, NCCL_FLOAT64 = 8, NCCL_MIN = 3 };
 
 struct NcclApi {
     void* lib = nullptr;
@@ -84,11 +84,18 @@ HaloNccl* halo_create(const cfd2d_halo* d, int nc, int nc_ex, int device, std::s
     h->total_send = so;
     if (rs != nc_ex - nc) { if (err) *err = "sum(recv_count) != nc_ex - nc"; delete h; return nullptr; }
     for (int i = 0; i < so; i++) if (d->send_ind[i] < 0 || d->send_ind[i] >= nc) { if (err) *err = "send_ind entry is not an owned cell"; delete h; return nullptr; }
-    cudaSetDevice(device);
-    cudaMalloc(&h->d_send_ind, (size_t)(so ? so : 1) * sizeof(int));
-    cudaMalloc(&h->d_stage, (size_t)(so ? so : 1) * 2 * sizeof(double4));
-    cudaMalloc(&h->d_scalar, sizeof(double));
-    if (so) cudaMemcpy(h->d_send_ind, d->send_ind, (size_t)so * sizeof(int), cudaMemcpyHostToDevice);
+    {
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_send_ind, (size_t)(so ? so : 1) * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_stage, (size_t)(so ? so : 1) * 2 * sizeof(double4));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_scalar, sizeof(double));
+        if (e == cudaSuccess && so) e = cudaMemcpy(h->d_send_ind, d->send_ind, (size_t)so * sizeof(int), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            if (err) *err = std::string("halo_create: ") + cudaGetErrorString(e);
+            halo_destroy(h);
+            return nullptr;
+        }
+    }
     nccl_uid_t uid;
     memcpy(&uid, d->nccl_unique_id, sizeof uid);
     int r = g_nccl.CommInitRank(&h->comm, d->nranks, uid, d->rank);
@@ -129,6 +136,26 @@ int halo_allreduce_min(HaloNccl* h, double* v, cudaStream_t s) {
     NCCL_TRY(h, g_nccl.AllReduce(h->d_scalar, h->d_scalar, 1, NCCL_FLOAT64, NCCL_MIN, h->comm, s));
     cudaMemcpyAsync(v, h->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, s);
     if (cudaStreamSynchronize(s) != cudaSuccess) { h->error = "allreduce sync failed"; return CFD2D_ECUDA; }
+    return 0;
+}
+
+int halo_rank(const HaloNccl* h) { return h->rank; }
+int halo_nranks(const HaloNccl* h) { return h->nranks; }
+
+int halo_gather_bytes(HaloNccl* h, int root, const void* send, size_t nsend, void* recv, const size_t* counts, cudaStream_t s) {
+    if (root < 0 || root >= h->nranks) { h->error = "gather: bad root"; return CFD2D_EINVAL; }
+    NCCL_TRY(h, g_nccl.GroupStart());
+    if (h->rank == root) {
+        size_t off = 0;
+        for (int p = 0; p < h->nranks; p++) {
+            if (p != root && counts[p] > 0)
+                NCCL_TRY(h, g_nccl.Recv((char*)recv + off, counts[p], NCCL_UINT8, p, h->comm, s));
+            off += counts[p];
+        }
+    } else if (nsend > 0) {
+        NCCL_TRY(h, g_nccl.Send(send, nsend, NCCL_UINT8, root, h->comm, s));
+    }
+    NCCL_TRY(h, g_nccl.GroupEnd());
     return 0;
 }
 

@@ -18,4 +18,9 @@ void halo_destroy(HaloNccl* h);
 // exchange records of rec4 double4's per cell (1: U4, 2: G8) of `field` ([nc_ex] records)
 int halo_exchange(HaloNccl* h, double4* field, int rec4, cudaStream_t s, int64_t* launches);
 int halo_allreduce_min(HaloNccl* h, double* v, cudaStream_t s);
+// gather of byte blocks on `root` (Parallel::send/recv towards the root rank, global.cpp:607-659): every rank
+// contributes nsend bytes (device), root receives counts[p] bytes of rank p at recv + sum(counts[0..p))
+int halo_gather_bytes(HaloNccl* h, int root, const void* send, size_t nsend, void* recv, const size_t* counts, cudaStream_t s);
+int halo_rank(const HaloNccl* h);
+int halo_nranks(const HaloNccl* h);
 const char* halo_error(HaloNccl* h);

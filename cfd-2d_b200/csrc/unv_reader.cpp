@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -81,7 +83,24 @@ inline int ints(const char* b, const char* e, long long* out, int want) {
 
 extern "C" {
 
+static int unv_read_impl(const char* path, cfd2d_unv** out);
+
 int cfd2d_unv_read(const char* path, cfd2d_unv** out) {
+    // no C++ exception may cross the C ABI (std::bad_alloc / length_error on hostile input)
+    try {
+        return unv_read_impl(path, out);
+    } catch (const std::exception& ex) {
+        if (out) *out = nullptr;
+        cfd2d_set_create_error(std::string("cfd2d_unv_read: ") + ex.what());
+        return CFD2D_EINVAL;
+    } catch (...) {
+        if (out) *out = nullptr;
+        cfd2d_set_create_error("cfd2d_unv_read: unknown exception");
+        return CFD2D_EINVAL;
+    }
+}
+
+static int unv_read_impl(const char* path, cfd2d_unv** out) {
     if (!path || !out) { cfd2d_set_create_error("null argument"); return CFD2D_EINVAL; }
     *out = nullptr;
     FILE* f = fopen(path, "rb");
@@ -96,7 +115,8 @@ int cfd2d_unv_read(const char* path, cfd2d_unv** out) {
     Lines L(buf);
     if (!L.ln.empty() && L.ln.back().first >= buf.data() + sz) L.ln.pop_back();
 
-    cfd2d_unv* u = new cfd2d_unv();
+    std::unique_ptr<cfd2d_unv> uown(new cfd2d_unv());      // freed on every early return and on exceptions
+    cfd2d_unv* u = uown.get();
     // element label (0-based) -> +(cell index + 1) | -(edge element index + 1) | 0 = unknown
     std::vector<int64_t> elem;
     struct RawGroup { std::string name; std::vector<int64_t> labels; };
@@ -117,10 +137,15 @@ int cfd2d_unv_read(const char* path, cfd2d_unv** out) {
                 long r = next_nonblank();
                 if (r < 0) break;
                 if (k >= b1) { err = "2411: node record without coordinates"; return; }
-                const char* p = L.ln[k].first; ++k;
+                // both coordinates must sit on THIS line (the reference's sscanf("%lf %lf") stays on it too,
+                // MeshReaderSalomeUnv.cpp:283-290): strtod skips newlines, so bound it by the line end
+                const char* p = L.ln[k].first; const char* pe = L.ln[k].second; ++k;
                 char* q = nullptr;
                 double x = strtod(p, &q);
-                double y = strtod(q, &q);
+                if (q == p || q > pe) { err = "2411: bad coordinate line"; return; }
+                const char* q0 = q;
+                double y = strtod(q0, &q);
+                if (q == q0 || q > pe) { err = "2411: coordinate line with a single number"; return; }
                 u->xy.push_back(x); u->xy.push_back(y);
             }
         } else if (kind == 2412) {
@@ -131,6 +156,9 @@ int cfd2d_unv_read(const char* path, cfd2d_unv** out) {
                 if (ints(L.ln[r].first, L.ln[r].second, t, 2) != 2) { err = "2412: bad element record"; return; }
                 const long long label = t[0] - 1, fe = t[1];
                 if (label < 0) { err = "2412: element label < 1"; return; }
+                // labels index a flat table: bound them by what the file could possibly hold (one element
+                // takes >= 2 lines) times a generous factor, so a corrupt label cannot allocate gigabytes
+                if ((unsigned long long)label > 64ull * (unsigned long long)nl + 1024ull) { err = "2412: element label out of range"; return; }
                 if ((size_t)label >= elem.size()) elem.resize((size_t)label + 1 + elem.size() / 2, 0);
                 if (fe == 11) {
                     if (k + 1 >= b1) { err = "2412: truncated beam element"; return; }
@@ -161,6 +189,7 @@ int cfd2d_unv_read(const char* path, cfd2d_unv** out) {
                 long long t[8];
                 if (ints(L.ln[r].first, L.ln[r].second, t, 8) != 8) { err = "2467: bad group record"; return; }
                 const long long n = t[7];
+                if (n < 0 || (unsigned long long)n > 2ull * (unsigned long long)nl + 2ull) { err = "2467: bad entity count"; return; }
                 if (k >= b1) { err = "2467: group without a name"; return; }
                 const char* p = L.ln[k].first; const char* e = L.ln[k].second; ++k;
                 while (p < e && (*p == ' ' || *p == '\t')) ++p;
@@ -197,7 +226,7 @@ int cfd2d_unv_read(const char* path, cfd2d_unv** out) {
         }
     }
     if (err.empty() && inside && bstart < nl) parse_block(bstart, nl);
-    if (!err.empty()) { cfd2d_set_create_error(err); delete u; return CFD2D_EINVAL; }
+    if (!err.empty()) { cfd2d_set_create_error(err); return CFD2D_EINVAL; }
     std::sort(raw.begin(), raw.end(), [](const RawGroup& a, const RawGroup& b) { return a.name < b.name; });
     for (auto& g : raw) {
         cfd2d_unv::Group o;
@@ -210,7 +239,7 @@ int cfd2d_unv_read(const char* path, cfd2d_unv** out) {
         }
         u->groups.push_back(std::move(o));
     }
-    *out = u;
+    *out = uown.release();
     return CFD2D_OK;
 }
 

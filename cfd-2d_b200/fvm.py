@@ -134,6 +134,8 @@ def load_library() -> C.CDLL:
     lib.cfd2d_kat_calc_flux.argtypes = [C.c_int, C.c_int, _dp, C.c_double, C.c_int, _dp]
     lib.cfd2d_kat_rim_orig_fast.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _dp, _ip]
     lib.cfd2d_fvm_use_exact_riemann.argtypes = [H, C.c_int]
+    lib.cfd2d_fvm_snapshot_begin.argtypes = [H]
+    lib.cfd2d_fvm_snapshot_end.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cfd2d_kat_urs.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _dp]
     lib.cfd2d_fvm_profile.argtypes = [H, C.c_int, _dp, C.POINTER(C.c_int64)]
     lib.cfd2d_fvm_launch_count.argtypes = [H]
@@ -156,7 +158,7 @@ EXPORTS = [
     "cfd2d_fvm_create", "cfd2d_fvm_destroy", "cfd2d_fvm_set_state", "cfd2d_fvm_calc_time_step", "cfd2d_fvm_step",
     "cfd2d_fvm_step_async", "cfd2d_fvm_sync", "cfd2d_fvm_get_state", "cfd2d_fvm_get_primitive", "cfd2d_fvm_tau",
     "cfd2d_fvm_time", "cfd2d_fvm_calc_grad", "cfd2d_fvm_edge_fluxes", "cfd2d_kat_rim_orig", "cfd2d_kat_calc_flux", "cfd2d_kat_urs",
-    "cfd2d_kat_rim_orig_fast", "cfd2d_fvm_use_exact_riemann",
+    "cfd2d_kat_rim_orig_fast", "cfd2d_fvm_use_exact_riemann", "cfd2d_fvm_snapshot_begin", "cfd2d_fvm_snapshot_end", "cfd2d_fvm_gather_state",
     "cfd2d_fvm_profile", "cfd2d_fvm_launch_count", "cfd2d_fvm_set_stream", "cfd2d_fvm_use_graph",
     "cfd2d_fvm_use_fused", "cfd2d_fvm_plan_summary", "cfd2d_tiling_plan", "cfd2d_pipe_plan",
     "cfd2d_unv_read", "cfd2d_unv_counts", "cfd2d_unv_copy", "cfd2d_unv_group_name", "cfd2d_unv_group_counts",
@@ -287,6 +289,17 @@ class Solver:
         """Step layout: 0 / False = three sweeps per stage, 1 / True = one tile-fused kernel per RK stage
         (k_stage), 2 = the persistent, bulk-copy-fed tile kernel (k_stage_pipe).  All give the same bits."""
         self._chk(self.lib.cfd2d_fvm_use_fused(self.h, int(on)))
+
+    def snapshot_begin(self):
+        """Start an asynchronous copy of the current state to the host (FVM_TVD::save pipeline)."""
+        self._chk(self.lib.cfd2d_fvm_snapshot_begin(self.h))
+
+    def snapshot_end(self):
+        n = self.nc
+        ro, ru, rv, re, ct = (np.empty(n) for _ in range(5))
+        fl = np.empty(n, np.uint32)
+        self._chk(self.lib.cfd2d_fvm_snapshot_end(self.h, *[C.c_void_p(x.ctypes.data) for x in (ro, ru, rv, re, ct, fl)]))
+        return ro, ru, rv, re, ct, fl
 
     def use_exact_riemann(self, on: bool):
         """Godunov handles: True = rim_orig evaluated in the reference's operation order (rim_orig_dev),

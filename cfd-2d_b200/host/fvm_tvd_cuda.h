@@ -27,7 +27,7 @@
 class FVM_TVD_CUDA : public FVM_TVD
 {
 public:
-	FVM_TVD_CUDA() : h(NULL), device(0), flux(CFD2D_FLUX_GODUNOV), order(2) {}
+	FVM_TVD_CUDA() : h(NULL), device(0), flux(CFD2D_FLUX_GODUNOV), order(2), rank(0), nranks(1) {}
 	virtual void init(char * xmlFileName);
 	virtual void run();
 	virtual void done();
@@ -35,8 +35,19 @@ protected:
 	void upload();                 // Grid + tables -> cfd2d_fvm_create / set_state / calc_time_step
 	void download();               // device state -> ro, ru, rv, re, cTau, Cell::flag
 	void fail(const char * what);  // log("ERROR...") + EXIT(1), the reference's error style
+	void collectSnapshot(int saveStep);   // cfd2d_fvm_snapshot_end + the reference's save()
+	// ---- multi-rank (one process per GPU): Decomp's partition and renumbering, recomputed from the global
+	// mesh every rank has read (reference src/methods/decomp.cpp:86-292), checked against mesh/mesh.NNNN.proc
+	// when the DECOMP method has written them
+	void decomposeMesh();
+	bool checkProcFile();
 	cfd2d_fvm * h;
 	int device, flux, order;
+	int rank, nranks;
+	std::vector<int> part;                      // METIS part[] of the global mesh (decomp.cpp:104)
+	std::vector< std::vector<int> > owned;      // per rank: owned global cells, ascending
+	std::vector<int> gCells, gEdges;            // this rank: local -> global cell (owned + halo) / edge
+	std::vector<int> recvCount, sendCount, sendInd;   // Grid::recvCount / sendInd of this rank (grid.h:94-96)
 };
 
 // The reference CPU method with the one fix-up SURVEY.md F11 documents (Cell::flag is never

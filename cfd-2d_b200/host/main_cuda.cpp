@@ -5,10 +5,23 @@
 #include "fvm_tvd_cuda.h"
 #include "tinyxml.h"
 #include <ctime>
+#include <unistd.h>
+#include <string>
 
 int main(int argc, char** argv)
 {
 	Parallel::init(&argc, &argv);
+	if (Parallel::procCount > 1 && Parallel::procId > 0) {
+		// every rank runs the reference's serial init (global mesh, regions, save(0)): ranks > 0 do it in a
+		// private directory holding links to the inputs, so only rank 0 writes res_*.vtk / task.log in place
+		char tmpl[] = "/tmp/cfd2d_rankXXXXXX";
+		char * d = mkdtemp(tmpl);
+		char cwd[4096];
+		if (d && getcwd(cwd, sizeof cwd)) {
+			std::string cmd = std::string("for f in '") + cwd + "'/*; do ln -s \"$f\" '" + d + "'/ 2>/dev/null; done";
+			if (system(cmd.c_str()) == 0 && chdir(d) == 0 && !getenv("CFD2D_JOB_DIR")) setenv("CFD2D_JOB_DIR", cwd, 1);
+		}
+	}
 	hLog = fopen("task.log", "w");
 	const char * xml = argc > 1 ? argv[1] : "task.xml";
 	TiXmlDocument doc(xml);

@@ -142,6 +142,24 @@ int cfd2d_fvm_sync(cfd2d_fvm* h);
 int cfd2d_fvm_get_state(cfd2d_fvm* h, double* ro, double* ru, double* rv, double* re,
                         double* cTau, uint32_t* flag);
 
+/* The same without stalling the time loop (FVM_TVD::run saves every FILE_OUTPUT_STEP steps,
+ * fvm_tvd.cpp:452-455, and its ASCII VTK writer :501-600 dominates wall time at large N):
+ * snapshot_begin captures the state as of the steps enqueued so far and starts the device-to-host
+ * copy on a separate copy stream; the caller enqueues the next chunk (cfd2d_fvm_step_async), then
+ * snapshot_end waits for the copy only and fills the arrays (any pointer may be NULL) -- the file is
+ * written while the GPU runs the next chunk.  One snapshot may be outstanding.                      */
+int cfd2d_fvm_snapshot_begin(cfd2d_fvm* h);
+int cfd2d_fvm_snapshot_end(cfd2d_fvm* h, double* ro, double* ru, double* rv, double* re,
+                           double* cTau, uint32_t* flag);
+
+/* Multi-rank handles: collect the owned-cell state of every rank on rank `root` over NCCL -- what a
+ * parallel Method does with Parallel::send/recv (global.cpp:607-659) before its root rank writes the
+ * result file.  counts[nranks] = owned cells of each rank (collective: every rank calls it with the
+ * same root and counts); on root the arrays (size sum(counts), any may be NULL) receive the ranks'
+ * blocks one after the other, each in its rank's own cell order; other ranks may pass NULL arrays.   */
+int cfd2d_fvm_gather_state(cfd2d_fvm* h, int root, const int32_t* counts, double* ro, double* ru,
+                           double* rv, double* re, double* cTau, uint32_t* flag);
+
 /* Primitive fields FVM_TVD::save prints (convertConsToPar per cell, fvm_tvd.cpp:529-572),
  * converted on the device; any pointer may be NULL.                                               */
 int cfd2d_fvm_get_primitive(cfd2d_fvm* h, double* r, double* p, double* T, double* u, double* v,

@@ -63,6 +63,19 @@ def test_create_rejects_bad_arguments():
     assert e.value.code == -5          # CFD2D_EBC, fvm_tvd.cpp:706-710
 
 
+def test_create_rejects_unsorted_cell_edges():
+    """The slot order of cell_edges is the summation order (ascending edge id, as the reference's
+    readers produce it): a caller with another order is refused instead of silently getting other bits.
+    The check runs before any device work, so it is testable without a GPU."""
+    import dataclasses
+    c = cases.strip(4, 2)
+    ce = np.array(c.mesh.cell_edges, copy=True)
+    ce[0] = ce[0][::-1]
+    with pytest.raises(fvm.CFDError) as e:
+        fvm.Solver(dataclasses.replace(c.mesh, cell_edges=ce), c.task)
+    assert e.value.code == -1 and "ascending" in str(e.value)
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the
     contract's keys, the reference's own single-thread rate as `value`, zero copy bytes in `e2e`."""

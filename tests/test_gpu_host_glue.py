@@ -118,3 +118,59 @@ def test_python_method_mirror_writes_the_same_vtk_as_the_cpp_dropin():
         a = open(os.path.join(d_cpp, "res_%010d.vtk" % step)).read()
         b = open(os.path.join(d_py, "res_%010d.vtk" % step)).read()
         assert a == b, step
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(BIN), reason="host driver not built (needs the reference tree at build time)")
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_dropin_driver_multi_rank_equals_single_rank(nranks):
+    """Multi-GPU THROUGH the reference's Method boundary: N processes of the same cfd2d_cuda binary (one per
+    GPU, tools/launch_ranks.py), each running the reference's init on the global mesh, recomputing Decomp's
+    partition (bundled METIS) and renumbering in the glue, cross-checking it against the mesh/mesh.NNNN.proc
+    files the reference's own DECOMP method wrote, exchanging halos over NCCL, gathering on rank 0 which
+    writes res_*.vtk with the reference's writer.  The files must be BYTE-identical to the 1-GPU run's.
+    Needs >= nranks GPUs (skipped otherwise: NCCL refuses two ranks on one device)."""
+    if _ngpu() < nranks:
+        pytest.skip(f"needs {nranks} GPUs")
+    import ctypes
+    import sys
+    import xml.etree.ElementTree as ET
+    c = cases.channel(64, 32, jitter=0.2, shuffle=True)
+    c.task.p_max = 1.01e5                      # the limiter trips around the bump: remediation across the cut
+    c.task.STEP_MAX = 30
+    c.task.FILE_OUTPUT_STEP = 10
+    c.task.LOG_OUTPUT_STEP = 10
+    d1, dn = tempfile.mkdtemp(), tempfile.mkdtemp()
+    run_driver(c, "FVM_TVD_CUDA", d1)
+    c.task.method = "FVM_TVD_CUDA"
+    c.write(dn)
+    # the reference's own DECOMP method -> mesh/mesh.NNNN.proc (oracle/_ref ships prebuilt)
+    dlib = os.path.join(ROOT, "oracle", "_ref", "libcfd2d_ref_decomp.so")
+    if os.path.exists(dlib):
+        tree = ET.parse(os.path.join(dn, "task.xml"))
+        dec = ET.SubElement(tree.getroot(), "decomp")
+        ET.SubElement(dec, "processors", value=str(nranks))
+        tree.write(os.path.join(dn, "task_decomp.xml"))
+        os.makedirs(os.path.join(dn, "mesh"), exist_ok=True)
+        cwd = os.getcwd()
+        try:
+            assert ctypes.CDLL(dlib, mode=os.RTLD_LOCAL).ref_decomp_run(dn.encode(), b"task_decomp.xml") == 0
+        finally:
+            os.chdir(cwd)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "launch_ranks.py"), str(nranks), BIN, "task.xml"],
+                       cwd=dn, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert f"rank 0/{nranks}" in r.stdout
+    if os.path.exists(dlib):
+        assert "partition maps equal mesh/mesh.0000.proc" in r.stdout
+    for step in (0, 10, 20, 30):
+        a = open(os.path.join(dn, "res_%010d.vtk" % step)).read()
+        b = open(os.path.join(d1, "res_%010d.vtk" % step)).read()
+        assert a == b, step
+    fin = read_vtk_cell_data(os.path.join(dn, "res_%010d.vtk" % 30))
+    assert np.isfinite(fin["Density"]).all()

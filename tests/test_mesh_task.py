@@ -134,3 +134,21 @@ def test_native_unv_reader_errors(tmp_path):
         unv.read_unv(p, native=True)
     with pytest.raises(ValueError, match="Unknown element type '44'"):
         unv.read_unv(p, native=False)
+
+
+def test_native_unv_reader_survives_hostile_input(tmp_path):
+    """no exception may cross the C ABI and no input may drive an unbounded allocation:
+    negative 2467 entity count, absurd 2412 element label, a 2411 coordinate line holding one number
+    (the reference's sscanf stays on the line; strtod would eat the next record's label)."""
+    from cfd2d_b200 import unv
+    D = "    -1\n"
+    cases_ = {
+        "neg_count": D + "  2467\n" + "         1         0         0         0         0         0         0        -5\nGRP\n" + D,
+        "huge_label": D + "  2412\n" + " 2000000000        41         2         1         7         3\n         1         2         3\n" + D,
+        "one_coord": D + "  2411\n" + "         1         1         1        11\n   1.0\n         2         1         1        11\n   2.0   3.0   0.0\n" + D,
+    }
+    for name, txt in cases_.items():
+        f = tmp_path / (name + ".unv")
+        f.write_text(txt)
+        with pytest.raises(ValueError):
+            unv.read_unv_native(str(f))
