@@ -6,6 +6,7 @@
 #include "fvm_fused.cuh"
 #include "fvm_pipe.cuh"
 #include "halo_nccl.h"
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges show up under nsys / ncu --nvtx, no-ops otherwise
 
 #include <algorithm>
 #include <cmath>
@@ -158,12 +159,17 @@ static RimC make_rim(double GAM) {
 }
 
 // ---- kernel launch helpers with optional per-kernel event timing ---------------------------
+struct NvtxScope { NvtxScope(const char* n) { nvtxRangePushA(n); } ~NvtxScope() { nvtxRangePop(); } };
+static const char* const k_names[CFD2D_NKERNELS] = {"k_grad", "k_flux", "k_update<1>", "k_update<2>", "k_remediate", "k_tau_steady",
+                                                     "halo exchange", "stage 1 (fused)", "stage 2 (fused)"};
 struct KTimer {
     cfd2d_fvm* h; int id; cudaStream_t st;
     KTimer(cfd2d_fvm* h_, int id_, cudaStream_t st_ = nullptr) : h(h_), id(id_), st(st_ ? st_ : h_->stream) {
+        nvtxRangePushA(k_names[id]);
         if (h->profiling) cudaEventRecord(h->ev0, st);
     }
     ~KTimer() {
+        nvtxRangePop();
         h->launches++;
         if (h->profiling) {
             cudaEventRecord(h->ev1, st);
@@ -1009,8 +1015,12 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     // phases expose more load latency than the three full-width sweeps hide; it stays selectable
     // (cfd2d_fvm_use_fused, CFD2D_FUSED=1) and is held to bit-identity with the sweeps by the tests.
     // Its plan (1-2 GB of tables at 4 M cells) is only built when it is selected.
+    // ---- default step layout per scheme, from the 4 M-cell measurements in profiles/README.md:
+    //   Godunov (FP64-issue bound): three sweeps -- the tile kernels lose to them on issue efficiency;
+    //   Lax-Friedrichs order 2: the pipelined tile kernel (2.5x fewer DRAM bytes, ~5 % faster);
+    //   Lax-Friedrichs order 1: the single cell-parallel sweep k_cell_lf1 (lf1_cell below).
     h->fused = false;
-    int layout = 0;
+    int layout = (c->flux == CFD2D_FLUX_LAX && c->order == 2) ? 2 : 0;
     if (const char* ev = getenv("CFD2D_FUSED")) layout = atoi(ev);
     h->fused = layout == 1;
     h->pm.reset(new HostMesh(std::move(pm)));
@@ -1300,6 +1310,7 @@ int cfd2d_pipe_plan(const cfd2d_mesh* m, int tile_cells, int dir_bins, int hilbe
 int cfd2d_fvm_set_state(cfd2d_fvm* h, const double* ro, const double* ru, const double* rv, const double* re,
                         const uint32_t* flag) {
     if (!h || !ro || !ru || !rv || !re) return CFD2D_EINVAL;
+    NvtxScope nv("cfd2d_fvm_set_state (H2D + pack)");
     CUDA_TRY(h, cudaSetDevice(h->device));
     size_t n = (size_t)h->nc * sizeof(double);
     const double* src[4] = {ro, ru, rv, re};
@@ -1361,6 +1372,7 @@ int cfd2d_fvm_calc_time_step(cfd2d_fvm* h, double* tau_out) {
 
 int cfd2d_fvm_step_async(cfd2d_fvm* h, int nsteps) {
     if (!h || nsteps < 0) return CFD2D_EINVAL;
+    NvtxScope nv("cfd2d_fvm_step (RK2 steps: FVM_TVD::run loop body)");
     CUDA_TRY(h, cudaSetDevice(h->device));
     int done = 0;
     if (h->use_graph && !h->profiling && h->halo)
@@ -1412,6 +1424,7 @@ int cfd2d_fvm_step(cfd2d_fvm* h, int nsteps) {
 
 int cfd2d_fvm_get_state(cfd2d_fvm* h, double* ro, double* ru, double* rv, double* re, double* cTau, uint32_t* flag) {
     if (!h || !ro || !ru || !rv || !re) return CFD2D_EINVAL;
+    NvtxScope nv("cfd2d_fvm_get_state (unpack + D2H)");
     CUDA_TRY(h, cudaSetDevice(h->device));
     size_t n = (size_t)h->nc * sizeof(double);
     if (h->nc) {

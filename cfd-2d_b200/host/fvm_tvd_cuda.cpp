@@ -7,6 +7,7 @@
 #include <fstream>
 #include <sstream>
 #include <cstdarg>
+#include <ctime>
 
 // The reference's log() (global.cpp:32-46) walks its va_list twice (vprintf, then vfprintf): with arguments
 // that is undefined behaviour and crashes on %s.  The glue therefore formats its own messages and passes
@@ -327,6 +328,8 @@ void FVM_TVD_CUDA::run()
 	double       t    = 0.0;
 	unsigned int step = 0;
 	int pendingSave = -1;
+	struct timespec t0;
+	clock_gettime(CLOCK_MONOTONIC, &t0);
 	while (t < TMAX && step < (unsigned int)STEP_MAX)
 	{
 		// how many steps until the next save / log line / end, exactly as the reference loop counts them
@@ -362,6 +365,16 @@ void FVM_TVD_CUDA::run()
 	}
 	if (pendingSave >= 0) collectSnapshot(pendingSave);
 	download();
+	{
+		// throughput in the project's metric: cell-updates/s per RK stage, and the 320 B/cell-stage
+		// algorithmic bandwidth it corresponds to; wall clock of the whole loop, output included
+		struct timespec t1;
+		clock_gettime(CLOCK_MONOTONIC, &t1);
+		const double wall = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+		const double cu = 2.0 * (double)grid.cCount * (double)step / (wall > 0 ? wall : 1);
+		glueLog("FVM_TVD_CUDA: %u steps of %d cells on %d GPU(s) in %.6f s (output included): %.4g cell-updates/s, %.1f GB/s algorithmic (320 B/cell-stage)\n",
+		        step, grid.cCount, nranks, wall, cu, cu * 320.0 / 1e9);
+	}
 }
 
 void FVM_TVD_CUDA::done()

@@ -89,11 +89,12 @@ def test_kat_calc_flux():
         assert (np.abs(god - g["godunov"]) / scale).max() < 1e-13, fx
 
 
-@pytest.mark.parametrize("variant", ["default", "exact_riemann", "pipe"])
+@pytest.mark.parametrize("variant", ["default", "sweeps", "exact_riemann", "pipe"])
 @pytest.mark.parametrize("name", list(pc.CASES))
 def test_run_matches_reference_golden_and_oracle(name, variant):
-    """variant: default = three sweeps + the reduced-instruction Riemann solver; exact_riemann = rim_orig in
-    the reference's operation order; pipe = the pipelined tile kernel (layout 2)."""
+    """variant: default = the library's choice for the scheme (Godunov: three sweeps + the reduced-instruction
+    Riemann solver; LF order 2: the pipelined tile kernel; LF order 1: k_cell_lf1); sweeps = layout 0;
+    exact_riemann = rim_orig in the reference's operation order; pipe = the pipelined tile kernel (layout 2)."""
     c, spec, st = pc.build(name)
     g = gold(name)
     exact = spec["flux"] == 1          # Lax-Friedrichs: no transcendental functions
@@ -104,6 +105,8 @@ def test_run_matches_reference_golden_and_oracle(name, variant):
         s.use_exact_riemann(True)
     if variant == "pipe":
         s.use_fused(2)
+    if variant == "sweeps":
+        s.use_fused(0)
     s.set_state(*st)
     tau = s.calc_time_step()
     assert tau == float(g["tau"])
