@@ -23,6 +23,7 @@ c.write(sys.argv[1])
 PY
 BIN=$PWD/cfd-2d_b200/host/_build/cfd2d_cuda
 CS=/usr/local/cuda/bin/compute-sanitizer
+if [ -z "${SKIP1:-}" ]; then
 for tool in memcheck racecheck; do
   for layout in 0 1 2; do
     for flux in GODUNOV LAX; do
@@ -33,6 +34,7 @@ for tool in memcheck racecheck; do
     done
   done
 done
+fi
 if [ "$NG" -ge 2 ]; then
   for tool in memcheck racecheck; do
     for layout in 0 2; do
