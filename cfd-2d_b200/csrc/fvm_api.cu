@@ -204,6 +204,13 @@ static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale, int e0 = 0
     if (!st) st = h->stream;
     KTimer t(h, CFD2D_K_FLUX, st);
     dim3 g(nblk(2 * (long long)(e1 - e0), 128)), b(128);   // one thread per (edge, Gauss point)
+#if CFD2D_FLUX_PERSIST
+    {   // persistent variant: one resident wave, blocks stride over the 64-edge chunks
+        int fxv = (h->ctrl.flux == CFD2D_FLUX_GODUNOV) ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB;
+        unsigned cap = (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * (unsigned)fxv;
+        if (g.x > cap) g.x = cap;
+    }
+#endif
     int fx = h->ctrl.flux, od = h->ctrl.order;
     if (fx == CFD2D_FLUX_GODUNOV && !h->exact_riemann) {
         if (od == 2) k_flux<2, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
@@ -1021,7 +1028,8 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     //   Lax-Friedrichs order 1: the single cell-parallel sweep k_cell_lf1 (lf1_cell below).
     h->fused = false;
     int layout = (c->flux == CFD2D_FLUX_LAX && c->order == 2) ? 2 : 0;
-    if (const char* ev = getenv("CFD2D_FUSED")) layout = atoi(ev);
+    bool layout_by_default = true;
+    if (const char* ev = getenv("CFD2D_FUSED")) { layout = atoi(ev); layout_by_default = false; }
     h->fused = layout == 1;
     h->pm.reset(new HostMesh(std::move(pm)));
     const HostMesh& pmr = *h->pm;
@@ -1100,7 +1108,13 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         TRY(cuda_rc(h, cudaEventCreateWithFlags(&h->ev_stage, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
         TRY(cuda_rc(h, cudaEventCreateWithFlags(&h->ev_U, cudaEventDisableTiming), "cudaEventCreateWithFlags"));
     }
-    if (layout == 2) { TRY(build_pipe_plan_dev(h)); h->pipe = true; }
+    if (layout == 2) {
+        int prc = build_pipe_plan_dev(h);
+        if (prc == CFD2D_OK) h->pipe = true;
+        else if (layout_by_default && prc == CFD2D_EINVAL) h->error.clear();   // e.g. a tile of an unordered mesh (CFD2D_HILBERT=0)
+                                                                               // whose rings exceed shared memory: three sweeps
+        else TRY(prc);
+    }
     TRY(cuda_rc(h, cudaDeviceSynchronize(), "cudaDeviceSynchronize (create)"));
 #undef TRY
     *out = h;

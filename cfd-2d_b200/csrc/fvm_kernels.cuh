@@ -51,21 +51,43 @@ struct KParams {
     const int* c_orig;      // [nc_ex] device -> caller
 };
 
+// A record is one 32-byte DRAM sector; sm_100 moves it with ONE 256-bit access (SASS LDG.E.ENL2.256 /
+// STG.E.ENL2.256, PTX ld/st.global.v4.f64) instead of two 128-bit ones: half the load/store
+// instructions and L1 tag look-ups in every sweep.  Records are 32-byte aligned (cudaMalloc base,
+// 32-byte stride).  CFD2D_LD256=0 keeps the two 16-byte accesses.
+#ifndef CFD2D_LD256
+#define CFD2D_LD256 1
+#endif
 __device__ __forceinline__ double4 ld4(const double4* __restrict__ p, int i) {
-    // two 16-byte loads of one 32-byte sector
+#if CFD2D_LD256
+    double4 v;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p + i));
+    return v;
+#else
     const double2* q = reinterpret_cast<const double2*>(p + i);
     double2 a = __ldg(q), b = __ldg(q + 1);
     return make_double4(a.x, a.y, b.x, b.y);
+#endif
 }
 __device__ __forceinline__ double4 ld4cg(const double4* p, int i) {
+#if CFD2D_LD256
+    double4 v;
+    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p + i) : "memory");
+    return v;
+#else
     const double2* q = reinterpret_cast<const double2*>(p + i);
     double2 a = __ldcg(q), b = __ldcg(q + 1);
     return make_double4(a.x, a.y, b.x, b.y);
+#endif
 }
 __device__ __forceinline__ void st4(double4* p, int i, double4 v) {
+#if CFD2D_LD256
+    asm volatile("st.global.v4.f64 [%4], {%0,%1,%2,%3};" :: "d"(v.x), "d"(v.y), "d"(v.z), "d"(v.w), "l"(p + i) : "memory");
+#else
     double2* q = reinterpret_cast<double2*>(p + i);
     q[0] = make_double2(v.x, v.y);
     q[1] = make_double2(v.z, v.w);
+#endif
 }
 
 __device__ __forceinline__ MatC get_mat(const KParams& P, int c) {
@@ -208,62 +230,77 @@ __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const 
 #ifndef CFD2D_FLUX_MINB
 #define CFD2D_FLUX_MINB 8
 #endif
-#ifndef CFD2D_FLUX_PRELOAD
-#define CFD2D_FLUX_PRELOAD 0
+#ifndef CFD2D_FLUX_SPLIT
+#define CFD2D_FLUX_SPLIT 1
 #endif
 
-template <int FLUX, int ORDER>
 #ifndef CFD2D_FLUXLF_MINB
 #define CFD2D_FLUXLF_MINB 8
 #endif
-__global__ void __launch_bounds__(128, FLUX != 1 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
-k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
-       const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2, int e0, int e1) {
-    // edges [e0, e1) of the device edge order (multi-rank handles: interior edges first, edges that
-    // touch a halo cell last, so the halo exchange overlaps the interior sweep)
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int e = e0 + (t >> 1);
-    const int gp = t & 1;
-    const bool live = e < e1;
-    if (!live) e = e1 - 1;
-    int2 cc = __ldg(P.e_c + e);
+#ifndef CFD2D_FLUX_PERSIST
+#define CFD2D_FLUX_PERSIST 0   // 1: persistent blocks, the {c1,c2} pair of the NEXT chunk is loaded one chunk ahead
+#endif
+
+// one (edge, Gauss point): `cc` = Edge::{c1,c2} already loaded, `park` = this thread's shared-memory slot
+template <int FLUX, int ORDER>
+__device__ __forceinline__ void flux_edge_gp(const KParams& P, const double4* __restrict__ W, const double4* __restrict__ G,
+                                             const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2,
+                                             int e, const int gp, const bool live, const int2 cc, volatile double* park) {
     double2 n = __ldg(P.e_n + e);
-#if CFD2D_FLUX_PRELOAD
-    // All gathers of BOTH cells are issued before any arithmetic (a boundary edge re-reads its own cell:
-    // same sectors, no extra traffic), so the kernel pays one exposed gather latency per thread instead
-    // of two; the records are consumed straight into the two reconstructed states.
+#if CFD2D_FLUX_SPLIT
+    // LANE SPLIT: the pair's lane 0 gathers cell c1, lane 1 gathers cell c2 -- each lane reads ONE
+    // cell's records (W, both gradient sectors, that cell's Gauss-point offsets) and reconstructs
+    // that cell's state at BOTH Gauss points; the state at the partner's Gauss point goes to the
+    // partner by shuffle.  Against "every lane gathers both cells" this issues the gathers of both
+    // cells at once (one exposed DRAM latency per thread instead of two: ncu put 24 % of this kernel's
+    // warp-stall samples on the second gather), and halves the gather instructions and L1 look-ups.
+    // Same expressions on the same operands => same bits.  On a boundary edge both lanes read c1.
     const bool inner = cc.y >= 0;
-    const int c2i = inner ? cc.y : cc.x;
-    double4 w1 = ld4(W, cc.x), w2 = ld4(W, c2i);
-    double4 ga1, gb1, ga2, gb2;
-    double2 d1, d2;
+    const bool second = gp && inner;
+    const int cell = second ? cc.y : cc.x;
+    double4 d = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (ORDER == 2) d = ld4(second ? P.e_d2 : P.e_d1, e);
+    // Edge::l * 0.5 is needed only after the solver; loaded NOW and parked in shared memory (a volatile
+    // store cannot be sunk), else the compiler moves the load next to its use and the whole DRAM
+    // latency is exposed at the end of every thread (11 % of the stall samples).
+    if (scale_by_l2) *park = __ldg(P.e_l2 + e);
+    const double4 w = ld4(W, cell);
+    double4 ga, gb;
+    if (ORDER == 2) { ga = ld4(G, 2 * cell); gb = ld4(G, 2 * cell + 1); }
+    double Eown = 0.0;
+    if (FLUX == 1) { double4 u = ld4(Ucur, cell); Eown = u.w / u.x; }
+    Prim M = {w.x, w.y, w.z, w.w};      // my cell at my Gauss point
+    Prim O = M;                          // my cell at the partner lane's Gauss point
+    if (ORDER == 2) {
+        const double mx = gp ? d.z : d.x, my = gp ? d.w : d.y;
+        const double ox = gp ? d.x : d.z, oy = gp ? d.y : d.w;
+        M.r += ga.x * mx + ga.y * my;
+        M.p += ga.z * mx + ga.w * my;
+        M.u += gb.x * mx + gb.y * my;
+        M.v += gb.z * mx + gb.w * my;
+        O.r += ga.x * ox + ga.y * oy;
+        O.p += ga.z * ox + ga.w * oy;
+        O.u += gb.x * ox + gb.y * oy;
+        O.v += gb.z * ox + gb.w * oy;
+    }
+    Prim X;                              // the partner's cell at my Gauss point
+    X.r = __shfl_xor_sync(0xffffffffu, O.r, 1);
+    X.p = __shfl_xor_sync(0xffffffffu, O.p, 1);
+    X.u = __shfl_xor_sync(0xffffffffu, O.u, 1);
+    X.v = __shfl_xor_sync(0xffffffffu, O.v, 1);
+    double EX = 0.0;
+    if (FLUX == 1) EX = __shfl_xor_sync(0xffffffffu, Eown, 1);
+    Prim L, R;
     double EL = 0.0, ER = 0.0;
-    if (ORDER == 2) {
-        ga1 = ld4(G, 2 * cc.x); gb1 = ld4(G, 2 * cc.x + 1);
-        ga2 = ld4(G, 2 * c2i); gb2 = ld4(G, 2 * c2i + 1);
-        d1 = __ldg(reinterpret_cast<const double2*>(P.e_d1 + e) + gp);
-        d2 = __ldg(reinterpret_cast<const double2*>(P.e_d2 + e) + gp);
-    }
-    if (FLUX == 1) {
-        double4 u1 = ld4(Ucur, cc.x), u2 = ld4(Ucur, c2i);
-        EL = u1.w / u1.x; ER = u2.w / u2.x;
-    }
-    Prim L = {w1.x, w1.y, w1.z, w1.w};
-    Prim R = {w2.x, w2.y, w2.z, w2.w};
-    double T1 = 0.0;
-    MatC m;
-    if (!inner) { m = get_mat(P, cc.x); T1 = prim_T(L, m); }   // cell-centre T, before extrapolation
-    if (ORDER == 2) {
-        L.r += ga1.x * d1.x + ga1.y * d1.y;
-        L.p += ga1.z * d1.x + ga1.w * d1.y;
-        L.u += gb1.x * d1.x + gb1.y * d1.y;
-        L.v += gb1.z * d1.x + gb1.w * d1.y;
-        R.r += ga2.x * d2.x + ga2.y * d2.y;
-        R.p += ga2.z * d2.x + ga2.w * d2.y;
-        R.u += gb2.x * d2.x + gb2.y * d2.y;
-        R.v += gb2.z * d2.x + gb2.w * d2.y;
-    }
-    if (!inner) {
+    if (inner) {
+        L.r = gp ? X.r : M.r; L.p = gp ? X.p : M.p; L.u = gp ? X.u : M.u; L.v = gp ? X.v : M.v;
+        R.r = gp ? M.r : X.r; R.p = gp ? M.p : X.p; R.u = gp ? M.u : X.u; R.v = gp ? M.v : X.v;
+        if (FLUX == 1) { EL = gp ? EX : Eown; ER = gp ? Eown : EX; }
+    } else {
+        L = M; EL = Eown;
+        MatC m = get_mat(P, cc.x);
+        Prim Lc = {w.x, w.y, w.z, w.w};
+        const double T1 = prim_T(Lc, m);                       // cell-centre T, before extrapolation
         int ib = __ldg(P.e_bc + e);
         R = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
     }
@@ -321,10 +358,47 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
     double sa = gp ? (pa + a) : (a + pa);            // (0.0 + f_gp1) + f_gp2
     double sb = gp ? (pb + b) : (b + pb);
     if (scale_by_l2) {
+#if CFD2D_FLUX_SPLIT
+        double l2 = *park;
+#else
         double l2 = __ldg(P.e_l2 + e);
+#endif
         sa = sa * l2; sb = sb * l2;
     }
     if (live) reinterpret_cast<double2*>(F + e)[gp] = make_double2(sa, sb);
+}
+
+template <int FLUX, int ORDER>
+__global__ void __launch_bounds__(128, FLUX != 1 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
+k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
+       const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2, int e0, int e1) {
+    // edges [e0, e1) of the device edge order (multi-rank handles: interior edges first, edges that
+    // touch a halo cell last, so the halo exchange overlaps the interior sweep)
+    __shared__ double s_park[128];
+    const int gp = threadIdx.x & 1;
+#if CFD2D_FLUX_PERSIST
+    // chunks of 64 edges, block-strided; Edge::{c1,c2} of the next chunk is in flight during this one
+    const int nchunk = (e1 - e0 + 63) >> 6;
+    int chunk = blockIdx.x;
+    if (chunk >= nchunk) return;
+    int e = e0 + (chunk << 6) + (threadIdx.x >> 1);
+    int2 cc_next = __ldg(P.e_c + (e < e1 ? e : e1 - 1));
+    for (; chunk < nchunk; chunk += gridDim.x) {
+        const bool live = e < e1;
+        const int ec = live ? e : e1 - 1;
+        const int2 cc = cc_next;
+        e += gridDim.x << 6;
+        if (chunk + gridDim.x < nchunk) cc_next = __ldg(P.e_c + (e < e1 ? e : e1 - 1));
+        flux_edge_gp<FLUX, ORDER>(P, W, G, Ucur, F, scale_by_l2, ec, gp, live, cc, s_park + threadIdx.x);
+    }
+#else
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int e = e0 + (t >> 1);
+    const bool live = e < e1;
+    if (!live) e = e1 - 1;
+    const int2 cc = __ldg(P.e_c + e);
+    flux_edge_gp<FLUX, ORDER>(P, W, G, Ucur, F, scale_by_l2, e, gp, live, cc, s_park + threadIdx.x);
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------
