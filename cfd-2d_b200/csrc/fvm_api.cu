@@ -204,22 +204,13 @@ static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale, int e0 = 0
     if (!st) st = h->stream;
     KTimer t(h, CFD2D_K_FLUX, st);
     dim3 g(nblk(2 * (long long)(e1 - e0), 128)), b(128);   // one thread per (edge, Gauss point)
-#if CFD2D_FLUX_PERSIST
-    {   // persistent variant: one resident wave, blocks stride over the 64-edge chunks
-        int fxv = (h->ctrl.flux == CFD2D_FLUX_GODUNOV) ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB;
-        unsigned cap = (unsigned)(h->sm_count > 0 ? h->sm_count : 148) * (unsigned)fxv;
-        if (g.x > cap) g.x = cap;
-    }
-#endif
-    int fx = h->ctrl.flux, od = h->ctrl.order;
-    if (fx == CFD2D_FLUX_GODUNOV && !h->exact_riemann) {
-        if (od == 2) k_flux<2, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
-        else k_flux<2, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
-    }
-    else if (fx == CFD2D_FLUX_GODUNOV && od == 2) k_flux<0, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
-    else if (fx == CFD2D_FLUX_GODUNOV) k_flux<0, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
-    else if (od == 2) k_flux<1, 2><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
-    else k_flux<1, 1><<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
+    const int fv = (h->ctrl.flux == CFD2D_FLUX_GODUNOV) ? (h->exact_riemann ? 0 : 2) : 1, od = h->ctrl.order;
+    typedef void (*flux_fn)(KParams, const double4*, const double4*, const double4*, double4*, int, int, int);
+    flux_fn f;
+    f = fv == 2 ? (od == 2 ? k_flux<2, 2> : k_flux<2, 1>)
+      : fv == 0 ? (od == 2 ? k_flux<0, 2> : k_flux<0, 1>)
+                : (od == 2 ? k_flux<1, 2> : k_flux<1, 1>);
+    f<<<g, b, 0, st>>>(h->P, h->W, h->G, Ucur, h->F, scale, e0, e1);
 }
 
 static void launch_update(cfd2d_fvm* h, int stage) {
@@ -1022,12 +1013,13 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     // phases expose more load latency than the three full-width sweeps hide; it stays selectable
     // (cfd2d_fvm_use_fused, CFD2D_FUSED=1) and is held to bit-identity with the sweeps by the tests.
     // Its plan (1-2 GB of tables at 4 M cells) is only built when it is selected.
-    // ---- default step layout per scheme, from the 4 M-cell measurements in profiles/README.md:
-    //   Godunov (FP64-issue bound): three sweeps -- the tile kernels lose to them on issue efficiency;
-    //   Lax-Friedrichs order 2: the pipelined tile kernel (2.5x fewer DRAM bytes, ~5 % faster);
-    //   Lax-Friedrichs order 1: the single cell-parallel sweep k_cell_lf1 (lf1_cell below).
+    // ---- default step layout, from the 4 M-cell measurements in profiles/README.md: three sweeps for
+    // every scheme but first-order Lax-Friedrichs (the single cell-parallel sweep k_cell_lf1, lf1_cell
+    // below).  With the lane-split k_flux and 256-bit record accesses the sweeps run LF order 2 in
+    // 0.99 ms per step against 1.11-1.18 for the pipelined tile kernel, which moves 2.5x fewer bytes but
+    // is bound by its instruction stream; Godunov was always faster as three sweeps.
     h->fused = false;
-    int layout = (c->flux == CFD2D_FLUX_LAX && c->order == 2) ? 2 : 0;
+    int layout = 0;
     bool layout_by_default = true;
     if (const char* ev = getenv("CFD2D_FUSED")) { layout = atoi(ev); layout_by_default = false; }
     h->fused = layout == 1;
@@ -1035,6 +1027,10 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
     const HostMesh& pmr = *h->pm;
     if (h->fused) TRY(build_fused_plan(h));
     if (const char* ev = getenv("CFD2D_EXACT_RIEMANN")) h->exact_riemann = atoi(ev) != 0;
+    {
+        int smc = 0;
+        if (cudaDeviceGetAttribute(&smc, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess) h->sm_count = smc;
+    }
     h->lf1_cell = (c->flux == CFD2D_FLUX_LAX && c->order == 1);
     if (const char* ev = getenv("CFD2D_LF1_CELL")) h->lf1_cell = h->lf1_cell && atoi(ev) != 0;
     if (!(halo && halo->nranks > 1)) {

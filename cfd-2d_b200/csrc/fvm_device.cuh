@@ -79,6 +79,16 @@ __device__ __forceinline__ Prim ghost_state(const Prim& pL, double TL, int kind,
     return pR;
 }
 
+// FVM_TVD::reconstruct (fvm_tvd.cpp:646-691): q += gq.x*DL.x + gq.y*DL.y.  FUSED = false keeps the
+// reference's rounding (mul, mul, add, add -- the Lax-Friedrichs variants and the order-faithful
+// Riemann statement are bit-exact through it); FUSED = true (only the reduced-instruction Godunov
+// path, which is held to 1e-12 and not to the bit) forms the same sum with two FMAs.
+template <bool FUSED>
+__device__ __forceinline__ double recon1(double q, double gx, double gy, double dx, double dy) {
+    if (FUSED) return fma(gy, dy, fma(gx, dx, q));   // explicit fma(): fused on the device whatever -fmad says
+    return q + (gx * dx + gy * dy);
+}
+
 // One side of the Newton function of rim_orig (global.cpp:281-304): given the trial pressure P
 // returns F and its derivative FS for the side with state (PS, CS, RCS).
 __device__ __forceinline__ void rim_side(const RimC& k, double P, double PS, double CS, double RCS,

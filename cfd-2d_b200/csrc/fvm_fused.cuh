@@ -144,10 +144,10 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
             if (ORDER == 2) {
                 double2 d = __ldg(reinterpret_cast<const double2*>(Q.e_d1 + eo) + gp);
                 double2 a = G0[l1], b = G1[l1], cc = G2[l1], dd = G3[l1];
-                L.r += a.x * d.x + a.y * d.y;
-                L.p += b.x * d.x + b.y * d.y;
-                L.u += cc.x * d.x + cc.y * d.y;
-                L.v += dd.x * d.x + dd.y * d.y;
+                L.r = recon1<FLUX == 2>(L.r, a.x, a.y, d.x, d.y);
+                L.p = recon1<FLUX == 2>(L.p, b.x, b.y, d.x, d.y);
+                L.u = recon1<FLUX == 2>(L.u, cc.x, cc.y, d.x, d.y);
+                L.v = recon1<FLUX == 2>(L.v, dd.x, dd.y, d.x, d.y);
             }
             if (inner) {
                 double2 va = W0[l2], vb = W1[l2];
@@ -156,10 +156,10 @@ k_stage(KParams P, FParams Q, const double4* __restrict__ W, const double4* Uin,
                 if (ORDER == 2) {
                     double2 d = __ldg(reinterpret_cast<const double2*>(Q.e_d2 + eo) + gp);
                     double2 a = G0[l2], b = G1[l2], cc = G2[l2], dd = G3[l2];
-                    R.r += a.x * d.x + a.y * d.y;
-                    R.p += b.x * d.x + b.y * d.y;
-                    R.u += cc.x * d.x + cc.y * d.y;
-                    R.v += dd.x * d.x + dd.y * d.y;
+                    R.r = recon1<FLUX == 2>(R.r, a.x, a.y, d.x, d.y);
+                    R.p = recon1<FLUX == 2>(R.p, b.x, b.y, d.x, d.y);
+                    R.u = recon1<FLUX == 2>(R.u, cc.x, cc.y, d.x, d.y);
+                    R.v = recon1<FLUX == 2>(R.v, dd.x, dd.y, d.x, d.y);
                 }
             } else {
                 int ib = -1 - __ldg(Q.e_c2 + eo);

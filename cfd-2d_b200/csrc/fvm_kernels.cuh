@@ -230,58 +230,39 @@ __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const 
 #ifndef CFD2D_FLUX_MINB
 #define CFD2D_FLUX_MINB 8
 #endif
-#ifndef CFD2D_FLUX_SPLIT
-#define CFD2D_FLUX_SPLIT 1
-#endif
-
 #ifndef CFD2D_FLUXLF_MINB
 #define CFD2D_FLUXLF_MINB 8
 #endif
-#ifndef CFD2D_FLUX_PERSIST
-#define CFD2D_FLUX_PERSIST 0   // 1: persistent blocks, the {c1,c2} pair of the NEXT chunk is loaded one chunk ahead
-#endif
 
-// one (edge, Gauss point): `cc` = Edge::{c1,c2} already loaded, `park` = this thread's shared-memory slot
+// LANE SPLIT: the pair's lane 0 gathers cell c1, lane 1 gathers cell c2 -- each lane reads ONE
+// cell's records (W, both gradient sectors, that cell's Gauss-point offsets `d`) and reconstructs
+// that cell's state at BOTH Gauss points; the state at the partner's Gauss point goes to the
+// partner by shuffle.  Against "every lane gathers both cells" this issues the gathers of both
+// cells at once (one exposed DRAM latency per thread instead of two: ncu put 24 % of the kernel's
+// warp-stall samples on the second gather), and halves the gather instructions and L1 look-ups.
+// Same expressions on the same operands => same bits.  On a boundary edge both lanes read c1.
+//
+// flux_gp_tail: everything after the loads.  w/ga/gb/d = this lane's cell records, Eown = its total
+// specific energy (LF only), l2slot = where Edge::l*0.5 of this edge is parked in shared memory.
 template <int FLUX, int ORDER>
-__device__ __forceinline__ void flux_edge_gp(const KParams& P, const double4* __restrict__ W, const double4* __restrict__ G,
-                                             const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2,
-                                             int e, const int gp, const bool live, const int2 cc, volatile double* park) {
-    double2 n = __ldg(P.e_n + e);
-#if CFD2D_FLUX_SPLIT
-    // LANE SPLIT: the pair's lane 0 gathers cell c1, lane 1 gathers cell c2 -- each lane reads ONE
-    // cell's records (W, both gradient sectors, that cell's Gauss-point offsets) and reconstructs
-    // that cell's state at BOTH Gauss points; the state at the partner's Gauss point goes to the
-    // partner by shuffle.  Against "every lane gathers both cells" this issues the gathers of both
-    // cells at once (one exposed DRAM latency per thread instead of two: ncu put 24 % of this kernel's
-    // warp-stall samples on the second gather), and halves the gather instructions and L1 look-ups.
-    // Same expressions on the same operands => same bits.  On a boundary edge both lanes read c1.
-    const bool inner = cc.y >= 0;
-    const bool second = gp && inner;
-    const int cell = second ? cc.y : cc.x;
-    double4 d = make_double4(0.0, 0.0, 0.0, 0.0);
-    if (ORDER == 2) d = ld4(second ? P.e_d2 : P.e_d1, e);
-    // Edge::l * 0.5 is needed only after the solver; loaded NOW and parked in shared memory (a volatile
-    // store cannot be sunk), else the compiler moves the load next to its use and the whole DRAM
-    // latency is exposed at the end of every thread (11 % of the stall samples).
-    if (scale_by_l2) *park = __ldg(P.e_l2 + e);
-    const double4 w = ld4(W, cell);
-    double4 ga, gb;
-    if (ORDER == 2) { ga = ld4(G, 2 * cell); gb = ld4(G, 2 * cell + 1); }
-    double Eown = 0.0;
-    if (FLUX == 1) { double4 u = ld4(Ucur, cell); Eown = u.w / u.x; }
+__device__ __forceinline__ void flux_gp_tail(const KParams& P, double4* __restrict__ F, int scale_by_l2, int e, const int gp,
+                                             const bool live, const bool inner, const int c1, const double2 n,
+                                             const double4 w, const double4 ga, const double4 gb, const double4 d,
+                                             const double Eown, const volatile double* l2slot) {
     Prim M = {w.x, w.y, w.z, w.w};      // my cell at my Gauss point
     Prim O = M;                          // my cell at the partner lane's Gauss point
     if (ORDER == 2) {
         const double mx = gp ? d.z : d.x, my = gp ? d.w : d.y;
         const double ox = gp ? d.x : d.z, oy = gp ? d.y : d.w;
-        M.r += ga.x * mx + ga.y * my;
-        M.p += ga.z * mx + ga.w * my;
-        M.u += gb.x * mx + gb.y * my;
-        M.v += gb.z * mx + gb.w * my;
-        O.r += ga.x * ox + ga.y * oy;
-        O.p += ga.z * ox + ga.w * oy;
-        O.u += gb.x * ox + gb.y * oy;
-        O.v += gb.z * ox + gb.w * oy;
+        constexpr bool FM = FLUX == 2;
+        M.r = recon1<FM>(M.r, ga.x, ga.y, mx, my);
+        M.p = recon1<FM>(M.p, ga.z, ga.w, mx, my);
+        M.u = recon1<FM>(M.u, gb.x, gb.y, mx, my);
+        M.v = recon1<FM>(M.v, gb.z, gb.w, mx, my);
+        O.r = recon1<FM>(O.r, ga.x, ga.y, ox, oy);
+        O.p = recon1<FM>(O.p, ga.z, ga.w, ox, oy);
+        O.u = recon1<FM>(O.u, gb.x, gb.y, ox, oy);
+        O.v = recon1<FM>(O.v, gb.z, gb.w, ox, oy);
     }
     Prim X;                              // the partner's cell at my Gauss point
     X.r = __shfl_xor_sync(0xffffffffu, O.r, 1);
@@ -298,49 +279,12 @@ __device__ __forceinline__ void flux_edge_gp(const KParams& P, const double4* __
         if (FLUX == 1) { EL = gp ? EX : Eown; ER = gp ? Eown : EX; }
     } else {
         L = M; EL = Eown;
-        MatC m = get_mat(P, cc.x);
+        MatC m = get_mat(P, c1);
         Prim Lc = {w.x, w.y, w.z, w.w};
         const double T1 = prim_T(Lc, m);                       // cell-centre T, before extrapolation
         int ib = __ldg(P.e_bc + e);
         R = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
     }
-#else
-    double4 w1 = ld4(W, cc.x);
-    Prim L = {w1.x, w1.y, w1.z, w1.w};
-    Prim R;
-    double EL = 0.0, ER = 0.0;
-    if (FLUX == 1) { double4 u = ld4(Ucur, cc.x); EL = u.w / u.x; }
-    const bool inner = cc.y >= 0;
-    double T1 = 0.0;
-    MatC m;
-    if (!inner) { m = get_mat(P, cc.x); T1 = prim_T(L, m); }   // cell-centre T, before extrapolation
-    if (ORDER == 2) {
-        const double2* dp = reinterpret_cast<const double2*>(P.e_d1 + e) + gp;
-        double2 d = __ldg(dp);
-        double4 ga = ld4(G, 2 * cc.x), gb = ld4(G, 2 * cc.x + 1);
-        L.r += ga.x * d.x + ga.y * d.y;
-        L.p += ga.z * d.x + ga.w * d.y;
-        L.u += gb.x * d.x + gb.y * d.y;
-        L.v += gb.z * d.x + gb.w * d.y;
-    }
-    if (inner) {
-        double4 w2 = ld4(W, cc.y);
-        R.r = w2.x; R.p = w2.y; R.u = w2.z; R.v = w2.w;
-        if (FLUX == 1) { double4 u = ld4(Ucur, cc.y); ER = u.w / u.x; }
-        if (ORDER == 2) {
-            const double2* dp = reinterpret_cast<const double2*>(P.e_d2 + e) + gp;
-            double2 d = __ldg(dp);
-            double4 ga = ld4(G, 2 * cc.y), gb = ld4(G, 2 * cc.y + 1);
-            R.r += ga.x * d.x + ga.y * d.y;
-            R.p += ga.z * d.x + ga.w * d.y;
-            R.u += gb.x * d.x + gb.y * d.y;
-            R.v += gb.z * d.x + gb.w * d.y;
-        }
-    } else {
-        int ib = __ldg(P.e_bc + e);
-        R = ghost_state(L, T1, P.bc_kind[ib], P.bc_par + 4 * ib, n.x, n.y, m, (FLUX == 1) ? &ER : nullptr);
-    }
-#endif
     double f0, f1, f2, f3;
     if (FLUX == 0) {
         int it = flux_godunov_dev(P.rim, P.max_newton, L, R, n.x, n.y, f0, f1, f2, f3);
@@ -358,16 +302,13 @@ __device__ __forceinline__ void flux_edge_gp(const KParams& P, const double4* __
     double sa = gp ? (pa + a) : (a + pa);            // (0.0 + f_gp1) + f_gp2
     double sb = gp ? (pb + b) : (b + pb);
     if (scale_by_l2) {
-#if CFD2D_FLUX_SPLIT
-        double l2 = *park;
-#else
-        double l2 = __ldg(P.e_l2 + e);
-#endif
+        double l2 = *l2slot;
         sa = sa * l2; sb = sb * l2;
     }
     if (live) reinterpret_cast<double2*>(F + e)[gp] = make_double2(sa, sb);
 }
 
+// K3, direct form: one thread per (edge, Gauss point), all loads issued up front.
 template <int FLUX, int ORDER>
 __global__ void __launch_bounds__(128, FLUX != 1 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
 k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
@@ -376,29 +317,28 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
     // touch a halo cell last, so the halo exchange overlaps the interior sweep)
     __shared__ double s_park[128];
     const int gp = threadIdx.x & 1;
-#if CFD2D_FLUX_PERSIST
-    // chunks of 64 edges, block-strided; Edge::{c1,c2} of the next chunk is in flight during this one
-    const int nchunk = (e1 - e0 + 63) >> 6;
-    int chunk = blockIdx.x;
-    if (chunk >= nchunk) return;
-    int e = e0 + (chunk << 6) + (threadIdx.x >> 1);
-    int2 cc_next = __ldg(P.e_c + (e < e1 ? e : e1 - 1));
-    for (; chunk < nchunk; chunk += gridDim.x) {
-        const bool live = e < e1;
-        const int ec = live ? e : e1 - 1;
-        const int2 cc = cc_next;
-        e += gridDim.x << 6;
-        if (chunk + gridDim.x < nchunk) cc_next = __ldg(P.e_c + (e < e1 ? e : e1 - 1));
-        flux_edge_gp<FLUX, ORDER>(P, W, G, Ucur, F, scale_by_l2, ec, gp, live, cc, s_park + threadIdx.x);
-    }
-#else
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int e = e0 + (t >> 1);
     const bool live = e < e1;
     if (!live) e = e1 - 1;
     const int2 cc = __ldg(P.e_c + e);
-    flux_edge_gp<FLUX, ORDER>(P, W, G, Ucur, F, scale_by_l2, e, gp, live, cc, s_park + threadIdx.x);
-#endif
+    const double2 n = __ldg(P.e_n + e);
+    const bool inner = cc.y >= 0;
+    const bool second = gp && inner;
+    const int cell = second ? cc.y : cc.x;
+    double4 d = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (ORDER == 2) d = ld4(second ? P.e_d2 : P.e_d1, e);
+    // Edge::l * 0.5 is needed only after the solver; loaded NOW and parked in shared memory (a volatile
+    // store cannot be sunk), else the compiler moves the load next to its use and the whole DRAM
+    // latency is exposed at the end of every thread (11 % of the stall samples).
+    volatile double* park = s_park + threadIdx.x;
+    if (scale_by_l2) *park = __ldg(P.e_l2 + e);
+    const double4 w = ld4(W, cell);
+    double4 ga = make_double4(0.0, 0.0, 0.0, 0.0), gb = ga;
+    if (ORDER == 2) { ga = ld4(G, 2 * cell); gb = ld4(G, 2 * cell + 1); }
+    double Eown = 0.0;
+    if (FLUX == 1) { double4 u = ld4(Ucur, cell); Eown = u.w / u.x; }
+    flux_gp_tail<FLUX, ORDER>(P, F, scale_by_l2, e, gp, live, inner, cc.x, n, w, ga, gb, d, Eown, park);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -94,13 +94,14 @@ __device__ __forceinline__ void pipe_issue_tile(const KParams& P, const PParams&
 #endif
 
 // reconstruction of one side at one Gauss point (FVM_TVD::reconstruct, fvm_tvd.cpp:646-691)
+template <bool FM>
 __device__ __forceinline__ Prim pipe_recon(const double2 wa, const double2 wb, const double2 a, const double2 b,
                                            const double2 c, const double2 d, double dx, double dy) {
     Prim q = {wa.x, wa.y, wb.x, wb.y};
-    q.r += a.x * dx + a.y * dy;
-    q.p += b.x * dx + b.y * dy;
-    q.u += c.x * dx + c.y * dy;
-    q.v += d.x * dx + d.y * dy;
+    q.r = recon1<FM>(q.r, a.x, a.y, dx, dy);
+    q.p = recon1<FM>(q.p, b.x, b.y, dx, dy);
+    q.u = recon1<FM>(q.u, c.x, c.y, dx, dy);
+    q.v = recon1<FM>(q.v, d.x, d.y, dx, dy);
     return q;
 }
 
@@ -338,8 +339,8 @@ k_stage_pipe(KParams P, PParams Q, const double4* Uin, double4* Uout, const doub
                 if (ORDER == 2) {
                     const double2 c1 = cxy[l1];
                     const double2 a = G0[l1], bq = G1[l1], cc = G2[l1], dd = G3[l1];
-                    La = pipe_recon(wa, wb, a, bq, cc, dd, pa.x - c1.x, pa.y - c1.y);   // DL = PE - P, fvm_tvd.cpp:661-664
-                    Lb = pipe_recon(wa, wb, a, bq, cc, dd, pb.x - c1.x, pb.y - c1.y);
+                    La = pipe_recon<FLUX == 2>(wa, wb, a, bq, cc, dd, pa.x - c1.x, pa.y - c1.y);   // DL = PE - P, fvm_tvd.cpp:661-664
+                    Lb = pipe_recon<FLUX == 2>(wa, wb, a, bq, cc, dd, pb.x - c1.x, pb.y - c1.y);
                 }
                 if (inner) {
                     const double2 va = W0[l2], vb = W1[l2];
@@ -348,8 +349,8 @@ k_stage_pipe(KParams P, PParams Q, const double4* Uin, double4* Uout, const doub
                     if (ORDER == 2) {
                         const double2 c2 = cxy[l2];
                         const double2 a = G0[l2], bq = G1[l2], cc = G2[l2], dd = G3[l2];
-                        Ra = pipe_recon(va, vb, a, bq, cc, dd, pa.x - c2.x, pa.y - c2.y);
-                        Rb = pipe_recon(va, vb, a, bq, cc, dd, pb.x - c2.x, pb.y - c2.y);
+                        Ra = pipe_recon<FLUX == 2>(va, vb, a, bq, cc, dd, pa.x - c2.x, pa.y - c2.y);
+                        Rb = pipe_recon<FLUX == 2>(va, vb, a, bq, cc, dd, pb.x - c2.x, pb.y - c2.y);
                     }
                 } else {
                     const int ib = l2 & 0xff;
@@ -389,7 +390,7 @@ k_stage_pipe(KParams P, PParams Q, const double4* Uin, double4* Uout, const doub
                 if (!inner) { m = mat_of(l1); T1 = prim_T(L, m); }   // cell-centre T, before extrapolation
                 if (ORDER == 2) {
                     const double2 c1 = cxy[l1];
-                    L = pipe_recon(wa, wb, G0[l1], G1[l1], G2[l1], G3[l1], pe.x - c1.x, pe.y - c1.y);
+                    L = pipe_recon<FLUX == 2>(wa, wb, G0[l1], G1[l1], G2[l1], G3[l1], pe.x - c1.x, pe.y - c1.y);
                 }
                 if (inner) {
                     const double2 va = W0[l2], vb = W1[l2];
@@ -397,7 +398,7 @@ k_stage_pipe(KParams P, PParams Q, const double4* Uin, double4* Uout, const doub
                     if (FLUX == 1) ER = Es[l2];
                     if (ORDER == 2) {
                         const double2 c2 = cxy[l2];
-                        Rr = pipe_recon(va, vb, G0[l2], G1[l2], G2[l2], G3[l2], pe.x - c2.x, pe.y - c2.y);
+                        Rr = pipe_recon<FLUX == 2>(va, vb, G0[l2], G1[l2], G2[l2], G3[l2], pe.x - c2.x, pe.y - c2.y);
                     }
                 } else {
                     const int ib = l2 & 0xff;
