@@ -174,27 +174,54 @@ __global__ void __launch_bounds__(256) k_tau_fill(KParams P, double tau) {
 // (the outward normal s*n reproduces the sign exactly) -- then the true division by S.  No atomics.
 // ---------------------------------------------------------------------------------------------
 // `list` (optional): only these n cells (multi-GPU: the cells whose gradients are sent to a peer).
-#ifndef CFD2D_GRAD_MINB
-#define CFD2D_GRAD_MINB 4     // 64 registers: 0.182 -> 0.174 ms at 4 M cells (profiles/README.md)
+#ifndef CFD2D_GRAD_GEOM_EARLY
+#define CFD2D_GRAD_GEOM_EARLY 1   // the nine slot-geometry loads are issued with the gathers, before any arithmetic
 #endif
+#ifndef CFD2D_GRAD_MINB
+#define CFD2D_GRAD_MINB 3     // 85 registers, no spills, 24 warps/SM with every load of a thread in flight at once:
+#endif                        // 0.144 ms at 4 M cells; 64 registers (32 warps, spills) 0.151; loads consumed slot by slot 0.162
 __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G,
                                               const int* __restrict__ list, int n) {
+    __shared__ double s_park[256];
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     if (list) c = __ldg(list + c);
-    double4 ws = ld4(W, c);
+    // Loads first, arithmetic after: the three neighbour ids, then ALL three neighbour records
+    // back-to-back (a boundary slot re-reads the cell's own record: same sector, no branch), so a
+    // thread pays one exposed gather latency, not one per slot (ncu: 62 % of the stall samples were
+    // long-scoreboard waits spread over four separate points).  The area is needed last; it is loaded
+    // with the rest and parked in shared memory so the compiler cannot sink the load next to its use.
+    int nb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) nb[k] = __ldg(P.s_nb + (size_t)k * P.nc + c);
+    const double4 ws = ld4(W, c);
+    double4 wnb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) wnb[k] = ld4(W, nb[k] >= 0 ? nb[k] : c);
+    volatile double* park = s_park + threadIdx.x;
+    *park = P.cell_S[c];
     double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+#if CFD2D_GRAD_GEOM_EARLY
+    double gnx[3], gny[3], gl[3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        int nb = __ldg(P.s_nb + (size_t)k * P.nc + c);
+        gnx[k] = __ldg(P.s_nx + (size_t)k * P.nc + c);
+        gny[k] = __ldg(P.s_ny + (size_t)k * P.nc + c);
+        gl[k] = __ldg(P.s_l + (size_t)k * P.nc + c);
+    }
+#endif
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+#if CFD2D_GRAD_GEOM_EARLY
+        double nx = gnx[k], ny = gny[k], l = gl[k];
+#else
         double nx = __ldg(P.s_nx + (size_t)k * P.nc + c);
         double ny = __ldg(P.s_ny + (size_t)k * P.nc + c);
         double l = __ldg(P.s_l + (size_t)k * P.nc + c);
-        double4 wn;
-        if (nb >= 0) {
-            wn = ld4(W, nb);
-        } else {
-            int ib = -1 - nb;
+#endif
+        double4 wn = wnb[k];
+        if (nb[k] < 0) {
+            int ib = -1 - nb[k];
             MatC m = get_mat(P, c);
             Prim pL = {ws.x, ws.y, ws.z, ws.w};
             Prim pR = ghost_state(pL, prim_T(pL, m), P.bc_kind[ib], P.bc_par + 4 * ib, nx, ny, m, nullptr);
@@ -206,7 +233,7 @@ __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const 
         g[4] += tu * nx * l; g[5] += tu * ny * l;
         g[6] += tv * nx * l; g[7] += tv * ny * l;
     }
-    double si = P.cell_S[c];
+    double si = *park;
     st4(G, 2 * c, make_double4(g[0] / si, g[1] / si, g[2] / si, g[3] / si));
     st4(G, 2 * c + 1, make_double4(g[4] / si, g[5] / si, g[6] / si, g[7] / si));
 }
@@ -355,9 +382,22 @@ __global__ void __launch_bounds__(256) k_update(KParams P, const double4* __rest
                                                 double4* Uout, double4* __restrict__ W) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.nc) return;
-    unsigned int fl = P.flag[c];
+    // every load of the thread is issued before the first branch: the flag test used to sit in front of
+    // the slot-table loads, a third dependent DRAM latency (flag -> slots -> fluxes) for a path that is
+    // almost never taken
+    const unsigned int fl = P.flag[c];
+    int es[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) es[k] = __ldg(P.s_es + (size_t)k * P.nc + c);
+    const double cfl = P.cfl[c];
+    double4 u = ld4cg(Uin, c);
+    double4 uo = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (STAGE == 2) uo = ld4cg(Uout, c);     // Ua: the state at step start (ro_old ...)
+    double4 f[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) f[k] = ld4cg(F, es[k] >> 1);
     if (fl & 2u) {                       // cellIsLim: frozen until remediated (:368, :421, :432)
-        if (STAGE == 1) st4(Uout, c, ld4cg(Uin, c));
+        if (STAGE == 1) st4(Uout, c, u);
         else {
             int pos = atomicAdd(P.err + 1, 1);
             if (pos < P.lim_cap) P.lim_list[pos] = __ldg(P.c_orig + c);
@@ -367,17 +407,12 @@ __global__ void __launch_bounds__(256) k_update(KParams P, const double4* __rest
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        int es = __ldg(P.s_es + (size_t)k * P.nc + c);
-        double4 f = ld4cg(F, es >> 1);
-        if (es & 1) { r0 += f.x; r1 += f.y; r2 += f.z; r3 += f.w; }
-        else        { r0 -= f.x; r1 -= f.y; r2 -= f.z; r3 -= f.w; }
+        if (es[k] & 1) { r0 += f[k].x; r1 += f[k].y; r2 += f[k].z; r3 += f[k].w; }
+        else           { r0 -= f[k].x; r1 -= f[k].y; r2 -= f[k].z; r3 -= f[k].w; }
     }
-    double cfl = P.cfl[c];
-    double4 u = ld4cg(Uin, c);
     u.x += cfl * r0; u.y += cfl * r1; u.z += cfl * r2; u.w += cfl * r3;
     MatC m = get_mat(P, c);
     if (STAGE == 2) {
-        double4 uo = ld4cg(Uout, c);     // Ua: the state at step start (ro_old ...)
         u.x = 0.5 * (uo.x + u.x); u.y = 0.5 * (uo.y + u.y); u.z = 0.5 * (uo.z + u.z); u.w = 0.5 * (uo.w + u.w);
     }
     Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);
@@ -407,7 +442,7 @@ __global__ void __launch_bounds__(256) k_update(KParams P, const double4* __rest
 // W is ping-ponged (neighbours still read the old primitive state).
 // ---------------------------------------------------------------------------------------------
 #ifndef CFD2D_LF1_MINB
-#define CFD2D_LF1_MINB 4     // 64 registers, 32 warps per SM: 0.369 -> 0.248 ms per stage at 4 M cells
+#define CFD2D_LF1_MINB 3     // registers for every load of a thread in flight at once (see k_grad)
 #endif
 template <int STAGE>
 __global__ void __launch_bounds__(256, CFD2D_LF1_MINB) k_cell_lf1(KParams P, const double4* __restrict__ W, const double4* Uin, double4* Uout,
@@ -416,39 +451,57 @@ __global__ void __launch_bounds__(256, CFD2D_LF1_MINB) k_cell_lf1(KParams P, con
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     if (list) c = __ldg(list + c);
-    unsigned int fl = P.flag[c];
+    // loads first (neighbour ids, then all neighbour records back-to-back, geometry), arithmetic after
+    const unsigned int fl = P.flag[c];
+    int nb[3], esb[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) { nb[k] = __ldg(P.s_nb + (size_t)k * P.nc + c); esb[k] = __ldg(P.s_es + (size_t)k * P.nc + c); }
+    const double4 wc = ld4(W, c);
+    double4 u = ld4cg(Uin, c);
+    double4 uo = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (STAGE == 2) uo = ld4cg(Uout, c);     // Ua: the state at step start (ro_old ...)
+    const double cfl = P.cfl[c];
+    double4 wnb[3];
+    double2 unb[3];                          // {rv, re} of the neighbour; its ro is W.r
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const int q = nb[k] >= 0 ? nb[k] : c;
+        wnb[k] = ld4(W, q);
+        unb[k] = __ldcg(reinterpret_cast<const double2*>(Uin + q) + 1);
+    }
+    double gnx[3], gny[3], gl[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const size_t o = (size_t)k * P.nc + c;
+        gnx[k] = __ldg(P.s_nx + o); gny[k] = __ldg(P.s_ny + o); gl[k] = __ldg(P.s_l + o);
+    }
     if (fl & 2u) {                       // cellIsLim: frozen until remediated (:368, :421, :432)
-        st4(Wout, c, ld4(W, c));
-        if (STAGE == 1) st4(Uout, c, ld4cg(Uin, c));
+        st4(Wout, c, wc);
+        if (STAGE == 1) st4(Uout, c, u);
         else {
             int pos = atomicAdd(P.err + 1, 1);
             if (pos < P.lim_cap) P.lim_list[pos] = __ldg(P.c_orig + c);
         }
         return;
     }
-    const double4 wc = ld4(W, c);
-    double4 u = ld4cg(Uin, c);
     const Prim own = {wc.x, wc.y, wc.z, wc.w};
     const double Eown = u.w / u.x;
     MatC m = get_mat(P, c);
     double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        const size_t o = (size_t)k * P.nc + c;
-        const int nb = __ldg(P.s_nb + o);
-        const double onx = __ldg(P.s_nx + o), ony = __ldg(P.s_ny + o);   // outward normal = +-Edge::n
-        const double l2 = __ldg(P.s_l + o) * 0.5;                        // fvm_tvd.cpp:335
-        const bool is_c2 = (__ldg(P.s_es + o) & 1) != 0;
+        const double onx = gnx[k], ony = gny[k];                         // outward normal = +-Edge::n
+        const double l2 = gl[k] * 0.5;                                   // fvm_tvd.cpp:335
+        const bool is_c2 = (esb[k] & 1) != 0;
         double f0, f1, f2, f3;
-        if (nb >= 0) {
-            const double4 wn = ld4(W, nb);
-            const double4 un = ld4cg(Uin, nb);
+        if (nb[k] >= 0) {
+            const double4 wn = wnb[k];
             const Prim oth = {wn.x, wn.y, wn.z, wn.w};
-            const double Eoth = un.w / un.x;
+            const double Eoth = unb[k].y / wn.x;                         // re / ro (W.r IS ro)
             if (is_c2) flux_lax_dev(P.rim.GAM, oth, Eoth, own, Eown, -onx, -ony, f0, f1, f2, f3);
             else       flux_lax_dev(P.rim.GAM, own, Eown, oth, Eoth, onx, ony, f0, f1, f2, f3);
         } else {
-            const int ib = -1 - nb;
+            const int ib = -1 - nb[k];
             double ER = 0.0;
             Prim R = ghost_state(own, prim_T(own, m), P.bc_kind[ib], P.bc_par + 4 * ib, onx, ony, m, &ER);
             flux_lax_dev(P.rim.GAM, own, Eown, R, ER, onx, ony, f0, f1, f2, f3);
@@ -457,10 +510,8 @@ __global__ void __launch_bounds__(256, CFD2D_LF1_MINB) k_cell_lf1(KParams P, con
         if (is_c2) { r0 += f0; r1 += f1; r2 += f2; r3 += f3; }
         else       { r0 -= f0; r1 -= f1; r2 -= f2; r3 -= f3; }
     }
-    double cfl = P.cfl[c];
     u.x += cfl * r0; u.y += cfl * r1; u.z += cfl * r2; u.w += cfl * r3;
     if (STAGE == 2) {
-        double4 uo = ld4cg(Uout, c);     // Ua: the state at step start (ro_old ...)
         u.x = 0.5 * (uo.x + u.x); u.y = 0.5 * (uo.y + u.y); u.z = 0.5 * (uo.z + u.z); u.w = 0.5 * (uo.w + u.w);
     }
     Prim w = cons_to_prim(u.x, u.y, u.z, u.w, m.gm1);

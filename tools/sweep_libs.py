@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Kernel-variant sweep: times the three-sweep layout with differently compiled libraries
-(CFD2D_LIB=<path>), one subprocess per library.  python tools/sweep_libs.py lib1.so lib2.so ..."""
+(CFD2D_LIB=<path>), one subprocess per library.  python tools/sweep_libs.py lib1.so lib2.so ...
+(SWEEP_CASES="flux:order,..." selects the schemes, default "0:2,1:2")"""
 import json
 import os
 import subprocess
@@ -15,7 +16,8 @@ from cfd2d_b200 import cases, fvm
 c = cases.channel(2000, 1000); st = c.smooth_state(); nc = c.mesh.nc
 stream = torch.cuda.Stream(); torch.cuda.set_stream(stream)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for flux, order in ((0, 2), (1, 2)):
+cases_ = [tuple(int(v) for v in x.split(':')) for x in os.environ.get('SWEEP_CASES', '0:2,1:2').split(',')]
+for flux, order in cases_:
     s = fvm.Solver(c.mesh, c.task, flux, order)
     s.set_stream(stream.cuda_stream); s.set_state(*st); s.calc_time_step(); s.step(10)
     torch.cuda.synchronize(); e0.record(stream); s.step_async(40); e1.record(stream); s.sync()
