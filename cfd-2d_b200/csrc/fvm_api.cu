@@ -189,12 +189,13 @@ static void launch_prim(cfd2d_fvm* h, const double4* U, double4* W, int c0, int 
 }
 
 // list == nullptr: all owned cells
-static void launch_grad(cfd2d_fvm* h, const int* list = nullptr, int n = -1, cudaStream_t st = nullptr) {
+// interior: all owned cells but those with a rank-halo neighbour (the boundary pass's list)
+static void launch_grad(cfd2d_fvm* h, const int* list = nullptr, int n = -1, cudaStream_t st = nullptr, bool interior = false) {
     if (!list && n < 0) n = h->nc;
     if (n <= 0) return;
     if (!st) st = h->stream;
     KTimer t(h, CFD2D_K_GRAD, st);
-    k_grad<<<nblk(n, 256), 256, 0, st>>>(h->P, h->W, h->G, list, n);
+    k_grad<<<nblk(n, 256), 256, 0, st>>>(h->P, h->W, h->G, list, n, interior ? 1 : 0);
 }
 
 // device edges [e0, e1); e1 < 0: all edges
@@ -361,7 +362,7 @@ static int enqueue_step_unfused(cfd2d_fvm* h) {
                 launch_grad(h, h->d_cells_bnd, h->n_cells_bnd, C);
                 if (ov) cudaEventRecord(h->ev_G, C);
                 if ((rc = exchange_G(h, C))) return rc;
-                launch_grad(h, h->d_cells_int, h->n_cells_int, S);
+                launch_grad(h, nullptr, -1, S, !h->diag_split || multi);   // diag_split on a serial handle keeps the list form
                 if (ov) cudaStreamWaitEvent(S, h->ev_G, 0);   // interior edges read the gradients of all owned cells
             }
             launch_flux(h, Ucur, 1, h->ne_int, h->ne, C);
@@ -407,7 +408,7 @@ static int enqueue_step_fused(cfd2d_fvm* h) {
         if (h->ctrl.order == 2) {
             if (h->n_send > 0) {
                 h->launches++;
-                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, Wcur, h->G, h->d_send_dev, h->n_send);
+                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, Wcur, h->G, h->d_send_dev, h->n_send, 0);
             }
             if ((rc = exchange_G(h, h->comm))) return rc;
         }
@@ -510,7 +511,7 @@ static int enqueue_step_pipe(cfd2d_fvm* h) {
             }
             if (h->n_send > 0) {
                 h->launches++;
-                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, h->W, h->G, h->d_send_dev, h->n_send);
+                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, h->W, h->G, h->d_send_dev, h->n_send, 0);
             }
             if ((rc = exchange_G(h, h->comm))) return rc;
         }
