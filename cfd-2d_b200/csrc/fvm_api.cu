@@ -195,7 +195,7 @@ static void launch_grad(cfd2d_fvm* h, const int* list = nullptr, int n = -1, cud
     if (n <= 0) return;
     if (!st) st = h->stream;
     KTimer t(h, CFD2D_K_GRAD, st);
-    k_grad<<<nblk(n, 256), 256, 0, st>>>(h->P, h->W, h->G, list, n, interior ? 1 : 0);
+    k_grad<<<nblk(n, CFD2D_GRAD_NT), CFD2D_GRAD_NT, 0, st>>>(h->P, h->W, h->G, list, n, interior ? 1 : 0);
 }
 
 // device edges [e0, e1); e1 < 0: all edges
@@ -204,7 +204,7 @@ static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale, int e0 = 0
     if (e1 <= e0) return;
     if (!st) st = h->stream;
     KTimer t(h, CFD2D_K_FLUX, st);
-    dim3 g(nblk(2 * (long long)(e1 - e0), 128)), b(128);   // one thread per (edge, Gauss point)
+    dim3 g(nblk(2 * (long long)(e1 - e0), CFD2D_FLUX_NT)), b(CFD2D_FLUX_NT);   // one thread per (edge, Gauss point)
     const int fv = (h->ctrl.flux == CFD2D_FLUX_GODUNOV) ? (h->exact_riemann ? 0 : 2) : 1, od = h->ctrl.order;
     typedef void (*flux_fn)(KParams, const double4*, const double4*, const double4*, double4*, int, int, int);
     flux_fn f;
@@ -217,8 +217,8 @@ static void launch_flux(cfd2d_fvm* h, const double4* Ucur, int scale, int e0 = 0
 static void launch_update(cfd2d_fvm* h, int stage) {
     if (h->nc == 0) return;
     KTimer t(h, stage == 1 ? CFD2D_K_UPDATE1 : CFD2D_K_UPDATE2);
-    if (stage == 1) k_update<1><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->F, h->Ua, h->Ub, h->W);
-    else k_update<2><<<nblk(h->nc, 256), 256, 0, h->stream>>>(h->P, h->F, h->Ub, h->Ua, h->W);
+    if (stage == 1) k_update<1><<<nblk(h->nc, CFD2D_UPDATE_NT), CFD2D_UPDATE_NT, 0, h->stream>>>(h->P, h->F, h->Ua, h->Ub, h->W);
+    else k_update<2><<<nblk(h->nc, CFD2D_UPDATE_NT), CFD2D_UPDATE_NT, 0, h->stream>>>(h->P, h->F, h->Ub, h->Ua, h->W);
 }
 
 static void launch_remediate(cfd2d_fvm* h) {
@@ -408,7 +408,7 @@ static int enqueue_step_fused(cfd2d_fvm* h) {
         if (h->ctrl.order == 2) {
             if (h->n_send > 0) {
                 h->launches++;
-                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, Wcur, h->G, h->d_send_dev, h->n_send, 0);
+                k_grad<<<nblk(h->n_send, CFD2D_GRAD_NT), CFD2D_GRAD_NT, 0, h->comm>>>(h->P, Wcur, h->G, h->d_send_dev, h->n_send, 0);
             }
             if ((rc = exchange_G(h, h->comm))) return rc;
         }
@@ -511,7 +511,7 @@ static int enqueue_step_pipe(cfd2d_fvm* h) {
             }
             if (h->n_send > 0) {
                 h->launches++;
-                k_grad<<<nblk(h->n_send, 256), 256, 0, h->comm>>>(h->P, h->W, h->G, h->d_send_dev, h->n_send, 0);
+                k_grad<<<nblk(h->n_send, CFD2D_GRAD_NT), CFD2D_GRAD_NT, 0, h->comm>>>(h->P, h->W, h->G, h->d_send_dev, h->n_send, 0);
             }
             if ((rc = exchange_G(h, h->comm))) return rc;
         }

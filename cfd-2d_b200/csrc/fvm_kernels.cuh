@@ -177,15 +177,21 @@ __global__ void __launch_bounds__(256) k_tau_fill(KParams P, double tau) {
 #ifndef CFD2D_GRAD_GEOM_EARLY
 #define CFD2D_GRAD_GEOM_EARLY 1   // the nine slot-geometry loads are issued with the gathers, before any arithmetic
 #endif
+#ifndef CFD2D_GRAD_NT
+#define CFD2D_GRAD_NT 64       // threads per block of k_grad: 256 -> 0.147, 128 -> 0.144, 64 -> 0.143 ms at 4 M cells
+#endif
+#ifndef CFD2D_UPDATE_NT
+#define CFD2D_UPDATE_NT 256
+#endif
 #ifndef CFD2D_GRAD_MINB
-#define CFD2D_GRAD_MINB 3     // 85 registers, no spills, 24 warps/SM with every load of a thread in flight at once:
+#define CFD2D_GRAD_MINB (768 / CFD2D_GRAD_NT)     // 85 registers, no spills, 24 warps/SM with every load of a thread in flight at once:
 #endif                        // 0.144 ms at 4 M cells; 64 registers (32 warps, spills) 0.151; loads consumed slot by slot 0.162
 // `skip_halo_adjacent` (multi-rank interior pass, list == nullptr): leave out the cells with a rank-halo
 // neighbour (id >= nc) -- they are the `list` of the boundary pass on the comm stream; the test costs no
 // memory traffic, whereas a 4-byte-per-cell interior list made this sweep 9 % slower.
-__global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G,
+__global__ void __launch_bounds__(CFD2D_GRAD_NT, CFD2D_GRAD_MINB) k_grad(KParams P, const double4* __restrict__ W, double4* __restrict__ G,
                                               const int* __restrict__ list, int n, int skip_halo_adjacent) {
-    __shared__ double s_park[256];
+    __shared__ double s_park[CFD2D_GRAD_NT];
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n) return;
     if (list) c = __ldg(list + c);
@@ -258,11 +264,15 @@ __global__ void __launch_bounds__(256, CFD2D_GRAD_MINB) k_grad(KParams P, const 
 // combined with one shuffle: fr = (0.0 + fr1) + fr2 in the reference; IEEE addition commutes, so
 // both lanes form the same sum bit for bit; lane 0 stores (fr,fu), lane 1 stores (fv,fe).
 // ---------------------------------------------------------------------------------------------
+#ifndef CFD2D_FLUX_NT
+#define CFD2D_FLUX_NT 64      // threads per block of k_flux: 256 -> 0.383, 128 -> 0.366, 64 -> 0.359, 32 -> 0.357 ms (Godunov, 4 M cells):
+                              // small blocks give their warp slots back sooner when Newton trip counts differ
+#endif
 #ifndef CFD2D_FLUX_MINB
-#define CFD2D_FLUX_MINB 8
+#define CFD2D_FLUX_MINB (1024 / CFD2D_FLUX_NT)     // 64 registers per thread
 #endif
 #ifndef CFD2D_FLUXLF_MINB
-#define CFD2D_FLUXLF_MINB 8
+#define CFD2D_FLUXLF_MINB (1024 / CFD2D_FLUX_NT)
 #endif
 
 // LANE SPLIT: the pair's lane 0 gathers cell c1, lane 1 gathers cell c2 -- each lane reads ONE
@@ -341,12 +351,12 @@ __device__ __forceinline__ void flux_gp_tail(const KParams& P, double4* __restri
 
 // K3, direct form: one thread per (edge, Gauss point), all loads issued up front.
 template <int FLUX, int ORDER>
-__global__ void __launch_bounds__(128, FLUX != 1 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
+__global__ void __launch_bounds__(CFD2D_FLUX_NT, FLUX != 1 ? CFD2D_FLUX_MINB : CFD2D_FLUXLF_MINB)
 k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
        const double4* __restrict__ Ucur, double4* __restrict__ F, int scale_by_l2, int e0, int e1) {
     // edges [e0, e1) of the device edge order (multi-rank handles: interior edges first, edges that
     // touch a halo cell last, so the halo exchange overlaps the interior sweep)
-    __shared__ double s_park[128];
+    __shared__ double s_park[CFD2D_FLUX_NT];
     const int gp = threadIdx.x & 1;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int e = e0 + (t >> 1);
@@ -382,7 +392,7 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
 // STAGE 1: Uout(=Ub) = Uin(=Ua) + cfl*R.     STAGE 2: Ua = 0.5*(Ua + (Ub + cfl*R)), flags.
 // ---------------------------------------------------------------------------------------------
 template <int STAGE>
-__global__ void __launch_bounds__(256) k_update(KParams P, const double4* __restrict__ F, const double4* Uin,
+__global__ void __launch_bounds__(CFD2D_UPDATE_NT) k_update(KParams P, const double4* __restrict__ F, const double4* Uin,
                                                 double4* Uout, double4* __restrict__ W) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= P.nc) return;
