@@ -1073,9 +1073,11 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         hd.send_ind = send_dev.data();
         h->halo = halo_create(&hd, nc, nc_ex, device, &herr);
         if (!h->halo) { g_create_error = herr; cfd2d_fvm_destroy(h); return CFD2D_ENCCL; }
-        // the step (both streams, fork/join through events, NCCL point-to-point included) is captured
-        // into one CUDA graph after two eager steps; CFD2D_GRAPH_MULTI=0 keeps it eager
-        h->use_graph = true;
+        // Multi-rank steps are launched eagerly: the host thread stays well ahead of the 1.2 ms of device
+        // work per step, and the captured two-stream graph (fork/join through events, NCCL point-to-point
+        // nodes) replays 3-4 % SLOWER than the same launches made directly (2 and 4 B200: 1.280 vs 1.243,
+        // 1.296 vs 1.243 ms per step, profiles/README.md section 4).  CFD2D_GRAPH_MULTI=1 captures it.
+        h->use_graph = false;
         if (const char* ev = getenv("CFD2D_GRAPH_MULTI")) h->use_graph = atoi(ev) != 0;
         h->n_send = nsend;
         { const int* q = nullptr; TRY(dev_upload(h, &q, send_dev)); h->d_send_dev = (int*)q; }

@@ -25,8 +25,12 @@ def main():
     # step layouts of a multi-rank handle: three sweeps with the halo exchange overlapped on the comm
     # stream (default), the same serialised on one stream, the tile-fused stage kernel, and the
     # pipelined tile kernel (interior tiles under the exchanges, boundary tiles after them)
-    modes = {"overlap": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1"}, "serial": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "0"},
-             "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1"}, "pipe": {"CFD2D_FUSED": "2", "CFD2D_OVERLAP": "1"}}
+    # "graph": the overlapped step captured into one two-stream CUDA graph (the default launches it eagerly)
+    modes = {"overlap": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "0"},
+             "graph": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "1"},
+             "serial": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "0", "CFD2D_GRAPH_MULTI": "0"},
+             "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "1"},
+             "pipe": {"CFD2D_FUSED": "2", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "0"}}
     # (partition, flux, order, steady, p_max): the last two cases lower the pressure limit below the
     # initial peak so that a blob of adjacent cells trips the limiter ACROSS the partition cut:
     # remediateLimCells (fvm_tvd.cpp:464-499) then rewrites send cells after the end-of-step exchange

@@ -29,4 +29,4 @@ def test_multi_gpu_equals_single_gpu_bitwise(n):
     sys.stdout.write(r.stdout[-4000:])
     sys.stderr.write(r.stderr[-4000:])
     assert r.returncode == 0
-    assert r.stdout.count("bitwise equal to 1 GPU = True") == 24      # 4 step layouts x 6 cases (2 trip the limiter across a cut)
+    assert r.stdout.count("bitwise equal to 1 GPU = True") == 30      # 5 step layouts x 6 cases (2 trip the limiter across a cut)
