@@ -525,6 +525,7 @@ def main():
             "config": workload_config(a), "clocks": clk, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "setup_s": setup_s}
     if halo_stats is not None:
+        halo_stats["transport"] = s.halo_transport
         line["halo"] = halo_stats
     if partition_note:
         line["config"]["partition_note"] = partition_note

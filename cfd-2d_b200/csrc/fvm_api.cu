@@ -1073,6 +1073,16 @@ int cfd2d_fvm_create(const cfd2d_mesh* m, const cfd2d_phys* p, const cfd2d_ctrl*
         hd.send_ind = send_dev.data();
         h->halo = halo_create(&hd, nc, nc_ex, device, &herr);
         if (!h->halo) { g_create_error = herr; cfd2d_fvm_destroy(h); return CFD2D_ENCCL; }
+        {   // halo transport: direct peer stores over NVLink (CUDA IPC) when CFD2D_HALO_P2P=1 and every rank can
+            // map its neighbours, else ncclSend/ncclRecv.  Collective: the variable must agree on all ranks.
+            int want = 0;
+            if (const char* ev = getenv("CFD2D_HALO_P2P")) want = atoi(ev);
+            if (want) {
+                double4* fields[3] = {h->Ua, h->Ub, h->G};
+                int prc = halo_p2p_enable(h->halo, fields, 3, h->stream);
+                if (prc) { g_create_error = halo_error(h->halo); cfd2d_fvm_destroy(h); return prc; }
+            }
+        }
         // Multi-rank steps are launched eagerly: the host thread stays well ahead of the 1.2 ms of device
         // work per step, and the captured two-stream graph (fork/join through events, NCCL point-to-point
         // nodes) replays 3-4 % SLOWER than the same launches made directly (2 and 4 B200: 1.280 vs 1.243,
@@ -1577,6 +1587,7 @@ int cfd2d_fvm_get_primitive(cfd2d_fvm* h, double* r, double* p, double* T, doubl
 double cfd2d_fvm_tau(const cfd2d_fvm* h) { return h ? h->TAU : 0.0; }
 double cfd2d_fvm_time(const cfd2d_fvm* h) { return h ? h->t : 0.0; }
 int64_t cfd2d_fvm_launch_count(const cfd2d_fvm* h) { return h ? h->launches : 0; }
+int cfd2d_fvm_halo_transport(const cfd2d_fvm* h) { return (!h || !h->halo) ? 0 : (halo_p2p_active(h->halo) ? 2 : 1); }
 
 int cfd2d_fvm_calc_grad(cfd2d_fvm* h, double* grad8) {
     if (!h || !grad8) return CFD2D_EINVAL;

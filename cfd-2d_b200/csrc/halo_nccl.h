@@ -14,6 +14,15 @@
 
 struct HaloNccl;
 HaloNccl* halo_create(const cfd2d_halo* d, int nc, int nc_ex, int device, std::string* err);
+// Direct peer-store transport for halo_exchange (NVLink / NVSwitch, CUDA IPC): every rank maps its
+// neighbours' copies of `fields` (each the base of its own cudaMalloc allocation, [nc_ex * rec4]
+// records) and a small flag array; halo_exchange(field in fields) then is ONE kernel that gathers
+// the send cells and stores them straight into the neighbours' halo slices, ordered by two flags per
+// neighbour (slice free / data landed, release-acquire at system scope) -- no staging buffer, no
+// ncclSend/ncclRecv rendezvous.  COLLECTIVE over the communicator.  Returns 0 and leaves the NCCL
+// transport in place when any rank cannot map a neighbour (no peer access, asymmetric lists).
+int halo_p2p_enable(HaloNccl* h, double4* const* fields, int nfields, cudaStream_t s);
+bool halo_p2p_active(const HaloNccl* h);
 void halo_destroy(HaloNccl* h);
 // exchange records of rec4 double4's per cell (1: U4, 2: G8) of `field` ([nc_ex] records)
 int halo_exchange(HaloNccl* h, double4* field, int rec4, cudaStream_t s, int64_t* launches);

@@ -140,6 +140,8 @@ def load_library() -> C.CDLL:
     lib.cfd2d_fvm_profile.argtypes = [H, C.c_int, _dp, C.POINTER(C.c_int64)]
     lib.cfd2d_fvm_launch_count.argtypes = [H]
     lib.cfd2d_fvm_launch_count.restype = C.c_int64
+    lib.cfd2d_fvm_halo_transport.argtypes = [H]
+    lib.cfd2d_fvm_halo_transport.restype = C.c_int
     lib.cfd2d_fvm_set_stream.argtypes = [H, C.c_void_p]
     lib.cfd2d_fvm_use_graph.argtypes = [H, C.c_int]
     lib.cfd2d_fvm_use_fused.argtypes = [H, C.c_int]
@@ -159,7 +161,7 @@ EXPORTS = [
     "cfd2d_fvm_step_async", "cfd2d_fvm_sync", "cfd2d_fvm_get_state", "cfd2d_fvm_get_primitive", "cfd2d_fvm_tau",
     "cfd2d_fvm_time", "cfd2d_fvm_calc_grad", "cfd2d_fvm_edge_fluxes", "cfd2d_kat_rim_orig", "cfd2d_kat_calc_flux", "cfd2d_kat_urs",
     "cfd2d_kat_rim_orig_fast", "cfd2d_fvm_use_exact_riemann", "cfd2d_fvm_snapshot_begin", "cfd2d_fvm_snapshot_end", "cfd2d_fvm_gather_state",
-    "cfd2d_fvm_profile", "cfd2d_fvm_launch_count", "cfd2d_fvm_set_stream", "cfd2d_fvm_use_graph",
+    "cfd2d_fvm_profile", "cfd2d_fvm_launch_count", "cfd2d_fvm_halo_transport", "cfd2d_fvm_set_stream", "cfd2d_fvm_use_graph",
     "cfd2d_fvm_use_fused", "cfd2d_fvm_plan_summary", "cfd2d_tiling_plan", "cfd2d_pipe_plan",
     "cfd2d_unv_read", "cfd2d_unv_counts", "cfd2d_unv_copy", "cfd2d_unv_group_name", "cfd2d_unv_group_counts",
     "cfd2d_unv_group_copy", "cfd2d_unv_free",
@@ -278,6 +280,11 @@ class Solver:
     @property
     def launch_count(self) -> int:
         return int(self.lib.cfd2d_fvm_launch_count(self.h))
+
+    @property
+    def halo_transport(self) -> str:
+        """how Method::exchange moves halo records on this handle"""
+        return {0: "none", 1: "nccl", 2: "peer-store"}[int(self.lib.cfd2d_fvm_halo_transport(self.h))]
 
     def set_stream(self, stream_ptr: int):
         self._chk(self.lib.cfd2d_fvm_set_stream(self.h, C.c_void_p(stream_ptr)))

@@ -212,6 +212,11 @@ int cfd2d_fvm_profile(cfd2d_fvm* h, int nsteps, double* ms, int64_t* launches);
 /* Kernel launches issued by this handle since create (the bench's gpu_launches claim).            */
 int64_t cfd2d_fvm_launch_count(const cfd2d_fvm* h);
 
+/* How this handle's Method::exchange (method.h:13-41) moves halo records: 0 serial handle, 1 NCCL
+ * send/recv, 2 direct peer stores over NVLink (CUDA IPC; CFD2D_HALO_P2P=1 at create on every rank,
+ * falls back to 1 when a neighbour cannot be mapped).                                             */
+int cfd2d_fvm_halo_transport(const cfd2d_fvm* h);
+
 /* Use an externally created cudaStream_t (e.g. the caller's current stream) for all launches.     */
 int cfd2d_fvm_set_stream(cfd2d_fvm* h, void* cuda_stream);
 

@@ -26,11 +26,17 @@ def main():
     # stream (default), the same serialised on one stream, the tile-fused stage kernel, and the
     # pipelined tile kernel (interior tiles under the exchanges, boundary tiles after them)
     # "graph": the overlapped step captured into one two-stream CUDA graph (the default launches it eagerly)
-    modes = {"overlap": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "0"},
-             "graph": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "1"},
-             "serial": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "0", "CFD2D_GRAPH_MULTI": "0"},
-             "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "1"},
-             "pipe": {"CFD2D_FUSED": "2", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "0"}}
+    modes = {"overlap": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "0", "CFD2D_HALO_P2P": "0"},
+             "graph": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "1", "CFD2D_HALO_P2P": "0"},
+             "serial": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "0", "CFD2D_GRAPH_MULTI": "0", "CFD2D_HALO_P2P": "0"},
+             "fused": {"CFD2D_FUSED": "1", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "1", "CFD2D_HALO_P2P": "0"},
+             "pipe": {"CFD2D_FUSED": "2", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "0", "CFD2D_HALO_P2P": "0"},
+             # halo records stored straight into the neighbours' arrays over NVLink (falls back to NCCL where a
+             # neighbour cannot be mapped; the line printed below names the transport that ran)
+             "p2p": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "0", "CFD2D_HALO_P2P": "1"},
+             "p2p_graph": {"CFD2D_FUSED": "0", "CFD2D_OVERLAP": "1", "CFD2D_GRAPH_MULTI": "1", "CFD2D_HALO_P2P": "1"}}
+    if os.environ.get("WORKER_MODES"):               # subset, e.g. WORKER_MODES=p2p,p2p_graph
+        modes = {k: v for k, v in modes.items() if k in os.environ["WORKER_MODES"].split(",")}
     # (partition, flux, order, steady, p_max): the last two cases lower the pressure limit below the
     # initial peak so that a blob of adjacent cells trips the limiter ACROSS the partition cut:
     # remediateLimCells (fvm_tvd.cpp:464-499) then rewrites send cells after the end-of-step exchange
@@ -52,6 +58,7 @@ def main():
         tau = s.calc_time_step()
         s.step(12)
         got = s.get_state()
+        transport = s.halo_transport
         rm = s.rank_mesh
         nflag = torch.zeros(world, dtype=torch.int64, device="cuda")
         nflag[rank] = int((got[5] != 0).sum())           # cells the limiter touched on this rank
@@ -87,7 +94,7 @@ def main():
                 good = ranks_hit >= 2 and flags_ok and (err == 0.0 if flux == 1 else err < 1e-12)
                 extra = f" limiter: touched cells per rank={nflag.tolist()} err_vs_oracle={err:.2e} flags_equal={flags_ok} ok={good}"
                 same = same and good
-            print(f"[multi-gpu x{world}] mode={mode} partition={partition} flux={flux} order={order} steady={steady} p_max={p_max}: "
+            print(f"[multi-gpu x{world}] mode={mode} ({transport}) partition={partition} flux={flux} order={order} steady={steady} p_max={p_max}: "
                   f"bitwise equal to 1 GPU = {same}, tau={tau}{extra}", flush=True)
             ok = ok and same
     flag = torch.tensor([1 if ok else 0], device="cuda")
