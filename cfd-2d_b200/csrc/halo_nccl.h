@@ -1,4 +1,5 @@
-// halo_nccl.h -- ghost-cell exchange of one rank over NCCL send/recv (NVLink 5 / NVSwitch).
+// halo_nccl.h -- ghost-cell exchange of one rank over NVLink 5 / NVSwitch: NCCL send/recv (default) or
+// direct peer stores into the neighbours' halo slices (halo_p2p_enable).
 //
 // Replaces Method::exchange (reference src/methods/method.h:13-127, MPI_Send/MPI_Recv per peer in
 // rank order, global.cpp:607-659): one pack kernel gathers the send lists of ALL peers into a
