@@ -90,6 +90,24 @@ __device__ __forceinline__ void st4(double4* p, int i, double4 v) {
 #endif
 }
 
+// L2 prefetch of one 128-byte line (hint; never faults).  CFD2D_<sweep>_PF_WAVES > 0: every block of a sweep asks
+// for the COALESCED tables (ids, geometry, own-cell records) of the block that will run in its place
+// that many resident waves later, so that block's first-level loads are L2 hits and only the gathers
+// they feed still pay a DRAM latency.
+// Measured at 4 M cells (profiles/r2zf, r2zg): k_grad -10 % at one wave (0.146 -> 0.130 ms), nothing at two (the lines are
+// gone again); k_update slower with it (it already runs at 81-92 % of the DRAM peak: the prefetches only add
+// requests); k_flux: see CFD2D_FLUX_PF_WAVES.
+#ifndef CFD2D_GRAD_PF_WAVES
+#define CFD2D_GRAD_PF_WAVES 1
+#endif
+#ifndef CFD2D_FLUX_PF_WAVES
+#define CFD2D_FLUX_PF_WAVES 0
+#endif
+#ifndef CFD2D_UPDATE_PF_WAVES
+#define CFD2D_UPDATE_PF_WAVES 0
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ MatC get_mat(const KParams& P, int c) {
     int im = (P.nmat > 1) ? (int)P.cell_mat[c] : 0;
     return P.mat[im];
@@ -193,6 +211,24 @@ __global__ void __launch_bounds__(CFD2D_GRAD_NT, CFD2D_GRAD_MINB) k_grad(KParams
                                               const int* __restrict__ list, int n, int skip_halo_adjacent) {
     __shared__ double s_park[CFD2D_GRAD_NT];
     int c = blockIdx.x * blockDim.x + threadIdx.x;
+#if CFD2D_GRAD_PF_WAVES
+    if (!list) {
+        constexpr int NT = CFD2D_GRAD_NT, LI = NT * 4 / 128, LD = NT * 8 / 128, LW = NT * 32 / 128;   // lines per table
+        const long long cb = ((long long)blockIdx.x + (long long)CFD2D_GRAD_PF_WAVES * 148 * CFD2D_GRAD_MINB) * NT;
+        if (cb + NT <= n) {
+            int t = threadIdx.x;
+            const char* q = nullptr;
+            if (t < 3 * LI) q = (const char*)(P.s_nb + (size_t)(t / LI) * P.nc + cb) + 128 * (t % LI);
+            else if ((t -= 3 * LI) < 9 * LD) {
+                const int tab = t / LD, k = tab % 3;
+                const double* base = tab < 3 ? P.s_nx : (tab < 6 ? P.s_ny : P.s_l);
+                q = (const char*)(base + (size_t)k * P.nc + cb) + 128 * (t % LD);
+            } else if ((t -= 9 * LD) < LD) q = (const char*)(P.cell_S + cb) + 128 * t;
+            else if ((t -= LD) < LW) q = (const char*)(W + cb) + 128 * t;
+            if (q) prefetch_l2(q);
+        }
+    }
+#endif
     if (c >= n) return;
     if (list) c = __ldg(list + c);
     // Loads first, arithmetic after: the three neighbour ids, then ALL three neighbour records
@@ -358,6 +394,23 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
     // touch a halo cell last, so the halo exchange overlaps the interior sweep)
     __shared__ double s_park[CFD2D_FLUX_NT];
     const int gp = threadIdx.x & 1;
+#if CFD2D_FLUX_PF_WAVES
+    {
+        constexpr int HB = CFD2D_FLUX_NT / 2;                 // edges per block
+        constexpr int L0 = HB * 8 / 128, L1 = L0 + HB * 16 / 128, L2 = L1 + HB * 32 / 128, L3 = L2 + HB * 32 / 128, L4 = L3 + HB * 8 / 128;
+        const long long eb = (long long)e0 + ((long long)blockIdx.x + (long long)CFD2D_FLUX_PF_WAVES * 148 * CFD2D_FLUX_MINB) * HB;
+        if (eb + HB <= e1) {
+            const int q = threadIdx.x;
+            const char* p = nullptr;
+            if (q < L0) p = (const char*)(P.e_c + eb) + 128 * q;
+            else if (q < L1) p = (const char*)(P.e_n + eb) + 128 * (q - L0);
+            else if (q < L2) { if (ORDER == 2) p = (const char*)(P.e_d1 + eb) + 128 * (q - L1); }
+            else if (q < L3) { if (ORDER == 2) p = (const char*)(P.e_d2 + eb) + 128 * (q - L2); }
+            else if (q < L4) { if (scale_by_l2) p = (const char*)(P.e_l2 + eb) + 128 * (q - L3); }
+            if (p) prefetch_l2(p);
+        }
+    }
+#endif
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int e = e0 + (t >> 1);
     const bool live = e < e1;
@@ -395,6 +448,22 @@ template <int STAGE>
 __global__ void __launch_bounds__(CFD2D_UPDATE_NT) k_update(KParams P, const double4* __restrict__ F, const double4* Uin,
                                                 double4* Uout, double4* __restrict__ W) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
+#if CFD2D_UPDATE_PF_WAVES
+    {
+        constexpr int NT = CFD2D_UPDATE_NT, LI = NT * 4 / 128, LD = NT * 8 / 128, LW = NT * 32 / 128;
+        const long long cb = ((long long)blockIdx.x + (long long)CFD2D_UPDATE_PF_WAVES * 148 * 4) * NT;
+        if (cb + NT <= P.nc) {
+            int t = threadIdx.x;
+            const char* q = nullptr;
+            if (t < LI) q = (const char*)(P.flag + cb) + 128 * t;
+            else if ((t -= LI) < 3 * LI) q = (const char*)(P.s_es + (size_t)(t / LI) * P.nc + cb) + 128 * (t % LI);
+            else if ((t -= 3 * LI) < LD) q = (const char*)(P.cfl + cb) + 128 * t;
+            else if ((t -= LD) < LW) q = (const char*)(Uin + cb) + 128 * t;
+            else if (STAGE == 2 && (t -= LW) < LW) q = (const char*)(Uout + cb) + 128 * t;
+            if (q) prefetch_l2(q);
+        }
+    }
+#endif
     if (c >= P.nc) return;
     // every load of the thread is issued before the first branch: the flag test used to sit in front of
     // the slot-table loads, a third dependent DRAM latency (flag -> slots -> fluxes) for a path that is
