@@ -96,7 +96,7 @@ __device__ __forceinline__ void st4(double4* p, int i, double4 v) {
 // they feed still pay a DRAM latency.
 // Measured at 4 M cells (profiles/r2zf, r2zg): k_grad -10 % at one wave (0.146 -> 0.130 ms), nothing at two (the lines are
 // gone again); k_update slower with it (it already runs at 81-92 % of the DRAM peak: the prefetches only add
-// requests); k_flux: see CFD2D_FLUX_PF_WAVES.
+// requests); k_flux: no gain at 1, 2 or 3 waves; k_cell_lf1: 0.455 -> 0.475 ms per step (code removed).
 #ifndef CFD2D_GRAD_PF_WAVES
 #define CFD2D_GRAD_PF_WAVES 1
 #endif
