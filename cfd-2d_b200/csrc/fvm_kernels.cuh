@@ -90,21 +90,16 @@ __device__ __forceinline__ void st4(double4* p, int i, double4 v) {
 #endif
 }
 
-// L2 prefetch of one 128-byte line (hint; never faults).  CFD2D_<sweep>_PF_WAVES > 0: every block of a sweep asks
-// for the COALESCED tables (ids, geometry, own-cell records) of the block that will run in its place
-// that many resident waves later, so that block's first-level loads are L2 hits and only the gathers
-// they feed still pay a DRAM latency.
-// Measured at 4 M cells (profiles/r2zf, r2zg): k_grad -10 % at one wave (0.146 -> 0.130 ms), nothing at two (the lines are
-// gone again); k_update slower with it (it already runs at 81-92 % of the DRAM peak: the prefetches only add
-// requests); k_flux: no gain at 1, 2 or 3 waves; k_cell_lf1: 0.455 -> 0.475 ms per step (code removed).
-#ifndef CFD2D_GRAD_PF_WAVES
-#define CFD2D_GRAD_PF_WAVES 1
-#endif
-#ifndef CFD2D_FLUX_PF_WAVES
-#define CFD2D_FLUX_PF_WAVES 0
-#endif
-#ifndef CFD2D_UPDATE_PF_WAVES
-#define CFD2D_UPDATE_PF_WAVES 0
+// L2 prefetch of one 128-byte line (hint; never faults).  Every block of k_grad asks for the COALESCED
+// tables (neighbour ids, slot geometry, areas, own-cell records) of the block CFD2D_GRAD_PF_BLOCKS further
+// on, which will run about half a resident wave later: that block's first-level loads are then L2 hits and
+// only the gathers they feed still pay a DRAM latency.
+// Measured at 4 M cells (profiles/r2zf ... r2zj): k_grad 0.143 -> 0.122 ms with the distance at half a resident wave
+// (one wave 0.127, two waves: nothing, the lines are gone again).  The same prefetch was tried and removed for
+// k_update (slower: it already runs at 81-92 % of the DRAM peak, the prefetches only add requests), k_flux (no
+// gain at 0.25 ... 3 waves: the first-level loads are a small part of its stalls) and k_cell_lf1 (slower).
+#ifndef CFD2D_GRAD_PF_BLOCKS
+#define CFD2D_GRAD_PF_BLOCKS 888   // 0: off
 #endif
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -211,10 +206,10 @@ __global__ void __launch_bounds__(CFD2D_GRAD_NT, CFD2D_GRAD_MINB) k_grad(KParams
                                               const int* __restrict__ list, int n, int skip_halo_adjacent) {
     __shared__ double s_park[CFD2D_GRAD_NT];
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-#if CFD2D_GRAD_PF_WAVES
+#if CFD2D_GRAD_PF_BLOCKS
     if (!list) {
         constexpr int NT = CFD2D_GRAD_NT, LI = NT * 4 / 128, LD = NT * 8 / 128, LW = NT * 32 / 128;   // lines per table
-        const long long cb = ((long long)blockIdx.x + (long long)CFD2D_GRAD_PF_WAVES * 148 * CFD2D_GRAD_MINB) * NT;
+        const long long cb = ((long long)blockIdx.x + (long long)CFD2D_GRAD_PF_BLOCKS) * NT;
         if (cb + NT <= n) {
             int t = threadIdx.x;
             const char* q = nullptr;
@@ -394,23 +389,6 @@ k_flux(KParams P, const double4* __restrict__ W, const double4* __restrict__ G,
     // touch a halo cell last, so the halo exchange overlaps the interior sweep)
     __shared__ double s_park[CFD2D_FLUX_NT];
     const int gp = threadIdx.x & 1;
-#if CFD2D_FLUX_PF_WAVES
-    {
-        constexpr int HB = CFD2D_FLUX_NT / 2;                 // edges per block
-        constexpr int L0 = HB * 8 / 128, L1 = L0 + HB * 16 / 128, L2 = L1 + HB * 32 / 128, L3 = L2 + HB * 32 / 128, L4 = L3 + HB * 8 / 128;
-        const long long eb = (long long)e0 + ((long long)blockIdx.x + (long long)CFD2D_FLUX_PF_WAVES * 148 * CFD2D_FLUX_MINB) * HB;
-        if (eb + HB <= e1) {
-            const int q = threadIdx.x;
-            const char* p = nullptr;
-            if (q < L0) p = (const char*)(P.e_c + eb) + 128 * q;
-            else if (q < L1) p = (const char*)(P.e_n + eb) + 128 * (q - L0);
-            else if (q < L2) { if (ORDER == 2) p = (const char*)(P.e_d1 + eb) + 128 * (q - L1); }
-            else if (q < L3) { if (ORDER == 2) p = (const char*)(P.e_d2 + eb) + 128 * (q - L2); }
-            else if (q < L4) { if (scale_by_l2) p = (const char*)(P.e_l2 + eb) + 128 * (q - L3); }
-            if (p) prefetch_l2(p);
-        }
-    }
-#endif
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int e = e0 + (t >> 1);
     const bool live = e < e1;
@@ -448,22 +426,6 @@ template <int STAGE>
 __global__ void __launch_bounds__(CFD2D_UPDATE_NT) k_update(KParams P, const double4* __restrict__ F, const double4* Uin,
                                                 double4* Uout, double4* __restrict__ W) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
-#if CFD2D_UPDATE_PF_WAVES
-    {
-        constexpr int NT = CFD2D_UPDATE_NT, LI = NT * 4 / 128, LD = NT * 8 / 128, LW = NT * 32 / 128;
-        const long long cb = ((long long)blockIdx.x + (long long)CFD2D_UPDATE_PF_WAVES * 148 * 4) * NT;
-        if (cb + NT <= P.nc) {
-            int t = threadIdx.x;
-            const char* q = nullptr;
-            if (t < LI) q = (const char*)(P.flag + cb) + 128 * t;
-            else if ((t -= LI) < 3 * LI) q = (const char*)(P.s_es + (size_t)(t / LI) * P.nc + cb) + 128 * (t % LI);
-            else if ((t -= 3 * LI) < LD) q = (const char*)(P.cfl + cb) + 128 * t;
-            else if ((t -= LD) < LW) q = (const char*)(Uin + cb) + 128 * t;
-            else if (STAGE == 2 && (t -= LW) < LW) q = (const char*)(Uout + cb) + 128 * t;
-            if (q) prefetch_l2(q);
-        }
-    }
-#endif
     if (c >= P.nc) return;
     // every load of the thread is issued before the first branch: the flag test used to sit in front of
     // the slot-table loads, a third dependent DRAM latency (flag -> slots -> fluxes) for a path that is
