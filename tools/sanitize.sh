@@ -35,6 +35,13 @@ for tool in memcheck racecheck; do
   done
 done
 fi
+if [ -z "${SKIP1:-}" ]; then      # first-order Lax-Friedrichs: the single cell-parallel sweep k_cell_lf1
+for tool in memcheck racecheck; do
+  ( cd $W && sed "s#</task>#<gpu flux=\"LAX\" order=\"1\"/></task>#" task.xml > t_LAX1.xml &&
+    timeout 600 $CS --tool $tool --error-exitcode 9 $BIN t_LAX1.xml ) > $OUT/sanitizer_${tool}_layout0_LAX_order1.log 2>&1
+  echo "exit $? $tool layout=0 flux=LAX order=1: $(grep -E 'ERROR SUMMARY|RACECHECK SUMMARY' $OUT/sanitizer_${tool}_layout0_LAX_order1.log | tail -1)"
+done
+fi
 if [ "$NG" -ge 2 ]; then
   for tool in memcheck racecheck; do
     for layout in 0 2; do
