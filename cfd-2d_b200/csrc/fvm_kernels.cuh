@@ -187,9 +187,6 @@ __global__ void __launch_bounds__(256) k_tau_fill(KParams P, double tau) {
 // (the outward normal s*n reproduces the sign exactly) -- then the true division by S.  No atomics.
 // ---------------------------------------------------------------------------------------------
 // `list` (optional): only these n cells (multi-GPU: the cells whose gradients are sent to a peer).
-#ifndef CFD2D_GRAD_GEOM_EARLY
-#define CFD2D_GRAD_GEOM_EARLY 1   // the nine slot-geometry loads are issued with the gathers, before any arithmetic
-#endif
 #ifndef CFD2D_GRAD_NT
 #define CFD2D_GRAD_NT 64       // threads per block of k_grad: 256 -> 0.147, 128 -> 0.144, 64 -> 0.143 ms at 4 M cells
 #endif
@@ -242,24 +239,16 @@ __global__ void __launch_bounds__(CFD2D_GRAD_NT, CFD2D_GRAD_MINB) k_grad(KParams
     volatile double* park = s_park + threadIdx.x;
     *park = P.cell_S[c];
     double g[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-#if CFD2D_GRAD_GEOM_EARLY
-    double gnx[3], gny[3], gl[3];
+    double gnx[3], gny[3], gl[3];      // the nine slot-geometry loads go out with the gathers, before any arithmetic
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         gnx[k] = __ldg(P.s_nx + (size_t)k * P.nc + c);
         gny[k] = __ldg(P.s_ny + (size_t)k * P.nc + c);
         gl[k] = __ldg(P.s_l + (size_t)k * P.nc + c);
     }
-#endif
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-#if CFD2D_GRAD_GEOM_EARLY
         double nx = gnx[k], ny = gny[k], l = gl[k];
-#else
-        double nx = __ldg(P.s_nx + (size_t)k * P.nc + c);
-        double ny = __ldg(P.s_ny + (size_t)k * P.nc + c);
-        double l = __ldg(P.s_l + (size_t)k * P.nc + c);
-#endif
         double4 wn = wnb[k];
         if (nb[k] < 0) {
             int ib = -1 - nb[k];
