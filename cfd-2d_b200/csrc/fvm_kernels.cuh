@@ -58,10 +58,16 @@ struct KParams {
 #ifndef CFD2D_LD256
 #define CFD2D_LD256 1
 #endif
+// L2 fill granularity of a record load: "" = the 32-byte sector asked for; ".L2::128B" / ".L2::256B" ask the
+// L2 to fetch the whole line(s) around it (SASS LDG...LTC128B / LTC256B) -- neighbouring records in Hilbert
+// order are wanted by neighbouring threads a moment later.  Measured: no effect either way (profiles/r2zm).
+#ifndef CFD2D_LD_L2HINT
+#define CFD2D_LD_L2HINT ""
+#endif
 __device__ __forceinline__ double4 ld4(const double4* __restrict__ p, int i) {
 #if CFD2D_LD256
     double4 v;
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p + i));
+    asm("ld.global.nc" CFD2D_LD_L2HINT ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p + i));
     return v;
 #else
     const double2* q = reinterpret_cast<const double2*>(p + i);
@@ -72,7 +78,7 @@ __device__ __forceinline__ double4 ld4(const double4* __restrict__ p, int i) {
 __device__ __forceinline__ double4 ld4cg(const double4* p, int i) {
 #if CFD2D_LD256
     double4 v;
-    asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p + i) : "memory");
+    asm volatile("ld.global.cg" CFD2D_LD_L2HINT ".v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p + i) : "memory");
     return v;
 #else
     const double2* q = reinterpret_cast<const double2*>(p + i);
