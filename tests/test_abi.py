@@ -35,6 +35,14 @@ def test_version_string():
     assert b"sm_100a" in lib.cfd2d_version()
 
 
+def test_null_handle_queries_are_safe():
+    """the query entry points take a NULL handle without touching the device"""
+    lib = fvm.load_library()
+    assert lib.cfd2d_fvm_halo_transport(None) == 0          # no handle: no halo, no transport
+    assert lib.cfd2d_fvm_launch_count(None) == 0
+    assert lib.cfd2d_fvm_plan_summary(None) in (b"", None)
+
+
 def _gpu():
     import torch
     return torch.cuda.is_available()
